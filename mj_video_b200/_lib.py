@@ -1,0 +1,73 @@
+"""ctypes binding of libmjv_b200.so (include/mjv_b200.h). No torch types cross this boundary: tensors are passed as
+raw device pointers + the current CUDA stream. The product path has NO fallback: if the library is missing this module
+raises at first use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libmjv_b200.so"
+_lib = None
+
+MJV_DTYPE_F32, MJV_DTYPE_BF16, MJV_DTYPE_F16 = 0, 1, 2
+EPI_STORE, EPI_GELU, EPI_RESID, EPI_SWIGLU, EPI_QKV_LLM, EPI_QKV_VIT, EPI_PATCH, EPI_SCATTER = range(8)
+
+
+class MjvError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("w", C.c_void_p), ("out", C.c_void_p),
+        ("lda", C.c_int64), ("ldw", C.c_int64), ("ldo", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("epilogue", C.c_int32), ("block_n", C.c_int32),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64), ("scale", C.c_void_p),
+        ("out_k", C.c_void_p), ("out_vt", C.c_void_p),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+        ("row_pos", C.c_void_p), ("row_map", C.c_void_p), ("pos_emb", C.c_void_p),
+        ("n_q_cols", C.c_int32), ("n_k_cols", C.c_int32),
+        ("vt_stride_head", C.c_int64), ("vt_ld", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32),
+    ]
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise loudly if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise MjvError(
+            f"{_LIB_PATH} is missing: build it with `python -m mj_video_b200.build` (or __graft_entry__.build()). "
+            "mj_video_b200 has no CPU/PyTorch fallback.")
+    lib = C.CDLL(str(_LIB_PATH))
+    lib.mjv_abi_version.restype = C.c_int
+    lib.mjv_last_error.restype = C.c_char_p
+    lib.mjv_launch_count.restype = C.c_longlong
+    lib.mjv_reset_launch_count.restype = None
+    lib.mjv_gemm_bf16.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+    lib.mjv_gemm_bf16.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().mjv_last_error()
+        raise MjvError(f"mjv error {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,100 @@
+// Host launcher for the tcgen05 GEMM family (see gemm_sm100.cuh).
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+#include "launch.cuh"
+
+namespace mjv {
+
+template <int BN, int EPI, int STAGES>
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, cudaStream_t stream) {
+    using L = gemm_detail::SmemLayout<BN, STAGES>;
+    auto kfn = gemm_bf16_tn_kernel<BN, EPI, STAGES>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        configured = true;
+    }
+    const int tiles = args.num_m_blocks * args.num_n_blocks;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    kfn<<<grid, gemm_detail::kThreads, L::kTotal, stream>>>(tmA, tmB, args);
+    MJV_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+template <int BN, int STAGES>
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t s) {
+    switch (epi) {
+        case EPI_STORE: return launch_gemm_t<BN, EPI_STORE, STAGES>(tmA, tmB, a, s);
+        case EPI_GELU: return launch_gemm_t<BN, EPI_GELU, STAGES>(tmA, tmB, a, s);
+        case EPI_RESID: return launch_gemm_t<BN, EPI_RESID, STAGES>(tmA, tmB, a, s);
+        case EPI_SWIGLU: return launch_gemm_t<BN, EPI_SWIGLU, STAGES>(tmA, tmB, a, s);
+        case EPI_QKV_LLM: return launch_gemm_t<BN, EPI_QKV_LLM, STAGES>(tmA, tmB, a, s);
+        case EPI_QKV_VIT: return launch_gemm_t<BN, EPI_QKV_VIT, STAGES>(tmA, tmB, a, s);
+        case EPI_PATCH: return launch_gemm_t<BN, EPI_PATCH, STAGES>(tmA, tmB, a, s);
+        case EPI_SCATTER: return launch_gemm_t<BN, EPI_SCATTER, STAGES>(tmA, tmB, a, s);
+        default: return set_error(MJV_ERR_ARG, "unknown GEMM epilogue %d", epi);
+    }
+}
+
+int gemm_bf16(const mjv_gemm_desc& d, cudaStream_t stream) {
+    MJV_CHECK(d.M > 0 && d.N > 0 && d.K > 0, MJV_ERR_ARG, "gemm: empty problem M=%d N=%d K=%d", d.M, d.N, d.K);
+    MJV_CHECK(d.lda % 8 == 0 && d.ldw % 8 == 0 && d.K % 8 == 0, MJV_ERR_ARG,
+              "gemm: lda/ldw/K must be multiples of 8 (lda=%lld ldw=%lld K=%d)", (long long)d.lda, (long long)d.ldw,
+              d.K);
+    int bn = d.block_n;
+    if (bn == 0) bn = (d.N % 256 == 0) ? 256 : 128;
+    MJV_CHECK((bn == 128 || bn == 256) && d.N % bn == 0, MJV_ERR_ARG, "gemm: N=%d not a multiple of block_n=%d", d.N,
+              bn);
+    if (d.epilogue == EPI_QKV_LLM) {
+        MJV_CHECK(d.n_q_cols % 128 == 0 && d.n_k_cols % 128 == 0 && d.rope_cos && d.rope_sin && d.row_pos &&
+                      d.out_k && d.out_vt,
+                  MJV_ERR_ARG, "gemm: QKV_LLM needs head_dim 128 and rope tables");
+    }
+    if (d.epilogue == EPI_QKV_VIT)
+        MJV_CHECK(d.bias && d.out_vt && d.seq > 0 && d.heads > 0, MJV_ERR_ARG, "gemm: QKV_VIT needs bias/out_vt");
+    if (d.epilogue == EPI_RESID) MJV_CHECK(d.residual != nullptr, MJV_ERR_ARG, "gemm: RESID needs residual");
+    if (d.epilogue == EPI_PATCH) MJV_CHECK(d.pos_emb && d.seq > 0, MJV_ERR_ARG, "gemm: PATCH needs pos_emb/seq");
+    if (d.epilogue == EPI_SCATTER) MJV_CHECK(d.row_map != nullptr, MJV_ERR_ARG, "gemm: SCATTER needs row_map");
+
+    CUtensorMap tmA, tmB;
+    MJV_PROPAGATE(make_tmap_2d(&tmA, d.a, (uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.lda, 128));
+    MJV_PROPAGATE(make_tmap_2d(&tmB, d.w, (uint64_t)d.N, (uint64_t)d.K, (uint64_t)d.ldw, (uint32_t)bn));
+
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = d.M;
+    a.N = d.N;
+    a.K = d.K;
+    a.num_m_blocks = (d.M + 127) / 128;
+    a.num_n_blocks = d.N / bn;
+    a.out = static_cast<__nv_bfloat16*>(d.out);
+    a.ldo = (int)d.ldo;
+    a.bias = static_cast<const __nv_bfloat16*>(d.bias);
+    a.residual = static_cast<const __nv_bfloat16*>(d.residual);
+    a.ldr = (int)d.ldr;
+    a.scale = static_cast<const __nv_bfloat16*>(d.scale);
+    a.out_k = static_cast<__nv_bfloat16*>(d.out_k);
+    a.out_vt = static_cast<__nv_bfloat16*>(d.out_vt);
+    a.rope_cos = d.rope_cos;
+    a.rope_sin = d.rope_sin;
+    a.row_pos = d.row_pos;
+    a.row_map = d.row_map;
+    a.pos = static_cast<const __nv_bfloat16*>(d.pos_emb);
+    a.n_q_cols = d.n_q_cols;
+    a.n_k_cols = d.n_k_cols;
+    a.vt_stride_head = d.vt_stride_head;
+    a.vt_ld = d.vt_ld;
+    a.seq = d.seq;
+    a.heads = d.heads;
+
+    if (bn == 256) return dispatch_epi<256, 4>(d.epilogue, tmA, tmB, a, stream);
+    return dispatch_epi<128, 6>(d.epilogue, tmA, tmB, a, stream);
+}
+
+}  // namespace mjv
+
+extern "C" int mjv_gemm_bf16(const mjv_gemm_desc* desc, void* stream) {
+    if (desc == nullptr) return mjv::set_error(MJV_ERR_ARG, "mjv_gemm_bf16: null desc");
+    return mjv::gemm_bf16(*desc, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,406 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] · W[N,K]^T  (+ fused epilogue)
+//
+//   * A (activations) and W (nn.Linear weight, [out,in]) are both K-major, loaded by TMA into 128B-swizzled
+//     shared-memory stages; tcgen05.mma (cta_group::1, M=128, N=BN, K=16) accumulates fp32 in TMEM.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM allocator,
+//     warps 4..7 = epilogue (TMEM -> registers -> fused math -> global).
+//   * two TMEM accumulator buffers (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+//   * static persistent schedule: tile = blockIdx.x + i * gridDim.x, n-fastest so co-resident CTAs share A rows
+//     and the whole W stays L2-resident.
+//
+// Epilogues cover the reference's call sites: K1 patch-embed, K4 ViT qkv, K7/K8 ViT proj/fc1/fc2,
+// K10 mlp1, K13+K14 LLM wqkv+RoPE, K16 wo, K17 SwiGLU. They mirror the reference's bf16 rounding points
+//  so the result tracks the reference's own bf16 forward, not just the fp32 ideal.
+#pragma once
+#include "ptx.cuh"
+
+namespace mjv {
+
+enum GemmEpilogue : int {
+    EPI_STORE = 0,    // out = bf16(acc + bias)
+    EPI_GELU = 1,     // out = bf16(gelu_erf(bf16(acc + bias)))
+    EPI_RESID = 2,    // out = bf16(res + bf16(bf16(acc + bias) * scale))        (bias/scale optional)
+    EPI_SWIGLU = 3,   // W rows interleaved [32 gate | 32 up]; out[:, j] = bf16(bf16(silu(g)) * u), N_out = N/2
+    EPI_QKV_LLM = 4,  // columns [q heads | k heads | v heads] x 128; RoPE on q,k; V written transposed
+    EPI_QKV_VIT = 5,  // columns [q | k | v] x (heads x 64); +bias; q,k -> qk[M,2*C]; V written transposed per tile
+    EPI_PATCH = 6,    // patch-embed: out row = m + m/P + 1, + bias + pos_emb[m%P + 1]
+    EPI_SCATTER = 7,  // out row = row_map[m]; out = bf16(acc + bias)
+};
+
+struct GemmArgs {
+    int M, N, K;
+    int num_m_blocks, num_n_blocks;
+    __nv_bfloat16* out;
+    int ldo;
+    const __nv_bfloat16* bias;      // [N] or null
+    const __nv_bfloat16* residual;  // [M, ldr] or null
+    int ldr;
+    const __nv_bfloat16* scale;  // [N] layer-scale or null
+    // specialised epilogues
+    __nv_bfloat16* out_k;      // QKV_LLM: K [M, n_kv*128]
+    __nv_bfloat16* out_vt;     // QKV_*: V^T
+    const float* rope_cos;     // [max_pos, 64]
+    const float* rope_sin;     // [max_pos, 64]
+    const int* row_pos;        // QKV_LLM: position id per packed token row
+    const int* row_map;        // SCATTER: destination row per m
+    const __nv_bfloat16* pos;  // PATCH: position embedding [P+1, N]
+    int n_q_cols;              // QKV: number of q columns
+    int n_k_cols;              // QKV: number of k columns
+    long long vt_stride_head;  // QKV: elements between consecutive (tile,)head planes of V^T ( = hd * vt_ld )
+    int vt_ld;                 // QKV: row stride of V^T (padded token count)
+    int seq;                   // QKV_VIT: tokens per tile (1025); PATCH: patches per tile (1024)
+    int heads;                 // QKV_VIT: heads
+};
+
+namespace gemm_detail {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    // 0.5*x*(1+erf(x/sqrt2)); erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution)
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    const float e = 1.0f - p * __expf(-z * z);
+    return 0.5f * x * (1.0f + copysignf(e, x));
+}
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void load32_bf16(const __nv_bfloat16* p, uint32_t* u) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 t = __ldg(q + i);
+        u[4 * i + 0] = t.x;
+        u[4 * i + 1] = t.y;
+        u[4 * i + 2] = t.z;
+        u[4 * i + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void store32_bf16(__nv_bfloat16* p, const uint32_t* u) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = make_uint4(u[4 * i + 0], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+};
+
+}  // namespace gemm_detail
+
+template <int BN, int EPI, int STAGES>
+__global__ void __launch_bounds__(gemm_detail::kThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmArgs args) {
+    using namespace gemm_detail;
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * L::kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = args.num_m_blocks * args.num_n_blocks;
+    const int nkb = (args.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&tmem_full[a], 1);
+            ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, 2 * BN);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / args.num_n_blocks) * BM;
+                const int n0 = (tile % args.num_n_blocks) * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                    ptx::tma_load_2d(sA + stage * L::kABytes, &tmA, &full_bar[stage], kb * BK, m0, ptx::kEvictNormal);
+                    ptx::tma_load_2d(sB + stage * L::kBBytes, &tmB, &full_bar[stage], kb * BK, n0, ptx::kEvictLast);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t adesc = ptx::make_desc_sw128(ptx::smem_u32(sA + stage * L::kABytes));
+                    const uint64_t bdesc = ptx::make_desc_sw128(ptx::smem_u32(sB + stage * L::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        ptx::mma_bf16_ss(d_tmem, ptx::desc_advance_k16(adesc, k), ptx::desc_advance_k16(bdesc, k),
+                                         idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::mma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    if (kb == nkb - 1) ptx::mma_commit(&tmem_full[acc]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue (warp%4 selects the TMEM lane quarter)
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / args.num_n_blocks) * BM;
+            const int n0 = (tile % args.num_n_blocks) * BN;
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < args.M;
+            ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t t_base = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+
+            if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_RESID || EPI == EPI_PATCH ||
+                          EPI == EPI_SCATTER) {
+                long long orow = row;
+                int prow = 0;
+                if constexpr (EPI == EPI_PATCH) {
+                    orow = row + row / args.seq + 1;
+                    prow = row % args.seq + 1;
+                }
+                if constexpr (EPI == EPI_SCATTER) orow = row_ok ? args.row_map[row] : 0;
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_x32(t_base + c, v);
+                    ptx::tmem_wait_ld();
+                    const int n = n0 + c;
+                    uint32_t o[16];
+                    uint32_t b[16];
+                    if (args.bias != nullptr) {
+                        load32_bf16(args.bias + n, b);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) b[i] = 0u;
+                    }
+                    if (row_ok) {
+                        uint32_t r[16], s[16];
+                        if constexpr (EPI == EPI_RESID) {
+                            load32_bf16(args.residual + static_cast<long long>(row) * args.ldr + n, r);
+                            if (args.scale != nullptr) load32_bf16(args.scale + n, s);
+                        }
+                        if constexpr (EPI == EPI_PATCH) load32_bf16(args.pos + static_cast<long long>(prow) * args.N + n, r);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float x0 = ptx::bf16_round(__uint_as_float(v[2 * i]) + ptx::bf16_lo(b[i]));
+                            float x1 = ptx::bf16_round(__uint_as_float(v[2 * i + 1]) + ptx::bf16_hi(b[i]));
+                            if constexpr (EPI == EPI_GELU) {
+                                x0 = gelu_erf(x0);
+                                x1 = gelu_erf(x1);
+                            }
+                            if constexpr (EPI == EPI_RESID) {
+                                if (args.scale != nullptr) {
+                                    x0 = ptx::bf16_round(x0 * ptx::bf16_lo(s[i]));
+                                    x1 = ptx::bf16_round(x1 * ptx::bf16_hi(s[i]));
+                                }
+                                x0 += ptx::bf16_lo(r[i]);
+                                x1 += ptx::bf16_hi(r[i]);
+                            }
+                            if constexpr (EPI == EPI_PATCH) {
+                                x0 += ptx::bf16_lo(r[i]);
+                                x1 += ptx::bf16_hi(r[i]);
+                            }
+                            o[i] = ptx::pack_bf16x2(x0, x1);
+                        }
+                        store32_bf16(args.out + orow * args.ldo + n, o);
+                    }
+                }
+            } else if constexpr (EPI == EPI_SWIGLU) {
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 64) {
+                    uint32_t g[32], u[32];
+                    ptx::tmem_ld_x32(t_base + c, g);
+                    ptx::tmem_ld_x32(t_base + c + 32, u);
+                    ptx::tmem_wait_ld();
+                    if (row_ok) {
+                        uint32_t o[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float g0 = ptx::bf16_round(__uint_as_float(g[2 * i]));
+                            const float g1 = ptx::bf16_round(__uint_as_float(g[2 * i + 1]));
+                            const float u0 = ptx::bf16_round(__uint_as_float(u[2 * i]));
+                            const float u1 = ptx::bf16_round(__uint_as_float(u[2 * i + 1]));
+                            o[i] = ptx::pack_bf16x2(ptx::bf16_round(silu(g0)) * u0, ptx::bf16_round(silu(g1)) * u1);
+                        }
+                        store32_bf16(args.out + static_cast<long long>(row) * args.ldo + ((n0 + c) >> 1), o);
+                    }
+                }
+            } else if constexpr (EPI == EPI_QKV_LLM) {
+                // head_dim 128: rotate-half pairs column j with j+64, i.e. chunk c with chunk c+2.
+                const int pos = row_ok ? args.row_pos[row] : 0;
+#pragma unroll 1
+                for (int h0 = 0; h0 < BN; h0 += 128) {
+                    const int n = n0 + h0;  // first column of this head
+                    if (n < args.n_q_cols + args.n_k_cols) {
+                        const bool is_q = n < args.n_q_cols;
+                        __nv_bfloat16* dst =
+                            is_q ? args.out + static_cast<long long>(row) * args.ldo + n
+                                 : args.out_k + static_cast<long long>(row) * args.n_k_cols + (n - args.n_q_cols);
+#pragma unroll 1
+                        for (int c = 0; c < 64; c += 32) {
+                            uint32_t x1[32], x2[32];
+                            ptx::tmem_ld_x32(t_base + h0 + c, x1);
+                            ptx::tmem_ld_x32(t_base + h0 + c + 64, x2);
+                            ptx::tmem_wait_ld();
+                            if (row_ok) {
+                                const float4* cs = reinterpret_cast<const float4*>(args.rope_cos + static_cast<long long>(pos) * 64 + c);
+                                const float4* sn = reinterpret_cast<const float4*>(args.rope_sin + static_cast<long long>(pos) * 64 + c);
+                                uint32_t o1[16], o2[16];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 cv = __ldg(cs + i);
+                                    const float4 sv = __ldg(sn + i);
+                                    const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
+                                    const float ss[4] = {sv.x, sv.y, sv.z, sv.w};
+                                    float a[4], b[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float p1 = ptx::bf16_round(__uint_as_float(x1[4 * i + j]));
+                                        const float p2 = ptx::bf16_round(__uint_as_float(x2[4 * i + j]));
+                                        // q*cos + rotate_half(q)*sin, each product and the sum rounded to bf16
+                                        a[j] = ptx::bf16_round(p1 * cc[j]) + ptx::bf16_round(-p2 * ss[j]);
+                                        b[j] = ptx::bf16_round(p2 * cc[j]) + ptx::bf16_round(p1 * ss[j]);
+                                    }
+                                    o1[2 * i] = ptx::pack_bf16x2(a[0], a[1]);
+                                    o1[2 * i + 1] = ptx::pack_bf16x2(a[2], a[3]);
+                                    o2[2 * i] = ptx::pack_bf16x2(b[0], b[1]);
+                                    o2[2 * i + 1] = ptx::pack_bf16x2(b[2], b[3]);
+                                }
+                                store32_bf16(dst + c, o1);
+                                store32_bf16(dst + c + 64, o2);
+                            }
+                        }
+                    } else {
+                        // V head: transposed store, V^T[head][d][token]
+                        const int vcol = n - args.n_q_cols - args.n_k_cols;  // head*128
+                        __nv_bfloat16* dst = args.out_vt + static_cast<long long>(vcol >> 7) * args.vt_stride_head + row;
+#pragma unroll 1
+                        for (int c = 0; c < 128; c += 32) {
+                            uint32_t v[32];
+                            ptx::tmem_ld_x32(t_base + h0 + c, v);
+                            ptx::tmem_wait_ld();
+                            if (row_ok) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    dst[static_cast<long long>(c + i) * args.vt_ld] = __float2bfloat16_rn(__uint_as_float(v[i]));
+                            }
+                        }
+                    }
+                }
+            } else if constexpr (EPI == EPI_QKV_VIT) {
+                const int t = row / args.seq;
+                const int s = row - t * args.seq;
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_x32(t_base + c, v);
+                    ptx::tmem_wait_ld();
+                    const int n = n0 + c;
+                    uint32_t b[16];
+                    load32_bf16(args.bias + n, b);
+                    if (row_ok) {
+                        if (n < args.n_q_cols + args.n_k_cols) {
+                            uint32_t o[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                o[i] = ptx::pack_bf16x2(__uint_as_float(v[2 * i]) + ptx::bf16_lo(b[i]),
+                                                        __uint_as_float(v[2 * i + 1]) + ptx::bf16_hi(b[i]));
+                            store32_bf16(args.out + static_cast<long long>(row) * args.ldo + n, o);
+                        } else {
+                            const int vcol = n - args.n_q_cols - args.n_k_cols;  // head*64 + d
+                            const int head = vcol >> 6;
+                            const int d0 = vcol & 63;
+                            __nv_bfloat16* dst = args.out_vt +
+                                                 (static_cast<long long>(t) * args.heads + head) * args.vt_stride_head +
+                                                 static_cast<long long>(d0) * args.vt_ld + s;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                dst[static_cast<long long>(2 * i) * args.vt_ld] =
+                                    __float2bfloat16_rn(__uint_as_float(v[2 * i]) + ptx::bf16_lo(b[i]));
+                                dst[static_cast<long long>(2 * i + 1) * args.vt_ld] =
+                                    __float2bfloat16_rn(__uint_as_float(v[2 * i + 1]) + ptx::bf16_hi(b[i]));
+                            }
+                        }
+                    }
+                }
+            }
+
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+}  // namespace mjv

@@ -87,6 +87,36 @@ typedef struct mjv_gemm_desc {
 
 int mjv_gemm_bf16(const mjv_gemm_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Primitive: fused softmax attention (tcgen05 QK^T and PV, online softmax, O accumulated in TMEM).
+ * Replaces flash_attn_varlen_qkvpacked_func(causal=False) (modeling_intern_vit.py:72-75; eager :210-227) and
+ * flash_attn_func / flash_attn_varlen_func(causal=True) with GQA (modeling_internlm2.py:498-561; eager :393-410).
+ *   batched mode (cu_seqlens == NULL): nseq sequences of seq_len rows; q,k rows = nseq*seq_len;
+ *       V^T planes = nseq*heads, each [head_dim][vt_ld] holding seq_len valid columns.
+ *   varlen  mode (cu_seqlens != NULL): packed rows; sequence s owns rows [cu[s], cu[s+1]); V^T planes = kv_heads,
+ *       each [head_dim][vt_ld] over the packed rows; `work` lists the (sequence, 128-row query block) items.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct mjv_attn_desc {
+    const void* q;        /* bf16 [rows, ldq]; head h occupies columns q_col0 + h*head_dim ...            */
+    const void* k;        /* bf16 [rows, ldk]; kv head g occupies columns k_col0 + g*head_dim ...         */
+    const void* vt;       /* bf16 V transposed                                                            */
+    void* out;            /* bf16 [rows, ldo]; head h occupies columns h*head_dim ...                     */
+    int64_t ldq, ldk, ldo;
+    int64_t vt_ld, vt_plane_stride;
+    int64_t total_rows;
+    int32_t head_dim;     /* 64 or 128                                                                    */
+    int32_t heads, kv_heads;
+    int32_t q_col0, k_col0;
+    int32_t causal;
+    int32_t nseq, seq_len;
+    const int32_t* cu_seqlens; /* device [nseq+1] or NULL                                                 */
+    const int32_t* work;       /* device int32[2*n_work] (seq, q_block) pairs or NULL                     */
+    int32_t n_work;
+    float scale;          /* softmax scale (1/sqrt(head_dim))                                             */
+} mjv_attn_desc;
+
+int mjv_attention(const mjv_attn_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

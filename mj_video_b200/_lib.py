@@ -33,6 +33,18 @@ class GemmDesc(C.Structure):
     ]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("vt", C.c_void_p), ("out", C.c_void_p),
+        ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldo", C.c_int64),
+        ("vt_ld", C.c_int64), ("vt_plane_stride", C.c_int64), ("total_rows", C.c_int64),
+        ("head_dim", C.c_int32), ("heads", C.c_int32), ("kv_heads", C.c_int32),
+        ("q_col0", C.c_int32), ("k_col0", C.c_int32), ("causal", C.c_int32),
+        ("nseq", C.c_int32), ("seq_len", C.c_int32),
+        ("cu_seqlens", C.c_void_p), ("work", C.c_void_p), ("n_work", C.c_int32), ("scale", C.c_float),
+    ]
+
+
 def lib_path() -> Path:
     return _LIB_PATH
 
@@ -53,6 +65,8 @@ def load() -> C.CDLL:
     lib.mjv_reset_launch_count.restype = None
     lib.mjv_gemm_bf16.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     lib.mjv_gemm_bf16.restype = C.c_int
+    lib.mjv_attention.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
+    lib.mjv_attention.restype = C.c_int
     _lib = lib
     return lib
 

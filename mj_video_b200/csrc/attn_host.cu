@@ -1,0 +1,95 @@
+// Host launcher for the tcgen05 attention kernels (see attn_sm100.cuh).
+#include "attn_sm100.cuh"
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace mjv {
+
+template <int HD, int BKV, bool CAUSAL>
+static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& a,
+                         dim3 grid, cudaStream_t stream) {
+    using L = attn_detail::Smem<HD, BKV>;
+    auto kfn = attention_kernel<HD, BKV, CAUSAL>;
+    static bool configured = false;
+    if (!configured) {
+        MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    kfn<<<grid, attn_detail::kThreads, L::kTotal, stream>>>(tq, tk, tv, a);
+    MJV_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int attention(const mjv_attn_desc& d, cudaStream_t stream) {
+    MJV_CHECK(d.head_dim == 64 || d.head_dim == 128, MJV_ERR_ARG, "attention: head_dim %d unsupported", d.head_dim);
+    MJV_CHECK(d.heads > 0 && d.kv_heads > 0 && d.heads % d.kv_heads == 0, MJV_ERR_ARG, "attention: bad head counts");
+    const bool varlen = d.cu_seqlens != nullptr;
+    if (varlen) MJV_CHECK(d.work != nullptr && d.n_work > 0, MJV_ERR_ARG, "attention: varlen mode needs a work list");
+    else MJV_CHECK(d.nseq > 0 && d.seq_len > 0, MJV_ERR_ARG, "attention: batched mode needs nseq/seq_len");
+    const int hd = d.head_dim;
+    const int bkv = hd == 64 ? 128 : 64;
+
+    CUtensorMap tq, tk, tv;
+    if (varlen) {
+        uint64_t qd[3] = {(uint64_t)(d.q_col0 + d.heads * hd), (uint64_t)d.total_rows, 1};
+        uint64_t qs[3] = {1, (uint64_t)d.ldq, (uint64_t)d.ldq * (uint64_t)d.total_rows};
+        uint32_t qb[3] = {64, 128, 1};
+        MJV_PROPAGATE(make_tmap_bf16(&tq, d.q, 3, qd, qs, qb));
+        uint64_t kd[3] = {(uint64_t)(d.k_col0 + d.kv_heads * hd), (uint64_t)d.total_rows, 1};
+        uint64_t ks[3] = {1, (uint64_t)d.ldk, (uint64_t)d.ldk * (uint64_t)d.total_rows};
+        uint32_t kb[3] = {64, (uint32_t)bkv, 1};
+        MJV_PROPAGATE(make_tmap_bf16(&tk, d.k, 3, kd, ks, kb));
+        uint64_t vd[3] = {(uint64_t)d.total_rows, (uint64_t)hd, (uint64_t)d.kv_heads};
+        uint64_t vs[3] = {1, (uint64_t)d.vt_ld, (uint64_t)d.vt_plane_stride};
+        uint32_t vb[3] = {64, (uint32_t)hd, 1};
+        MJV_PROPAGATE(make_tmap_bf16(&tv, d.vt, 3, vd, vs, vb));
+    } else {
+        uint64_t qd[3] = {(uint64_t)(d.q_col0 + d.heads * hd), (uint64_t)d.seq_len, (uint64_t)d.nseq};
+        uint64_t qs[3] = {1, (uint64_t)d.ldq, (uint64_t)d.ldq * (uint64_t)d.seq_len};
+        uint32_t qb[3] = {64, 128, 1};
+        MJV_PROPAGATE(make_tmap_bf16(&tq, d.q, 3, qd, qs, qb));
+        uint64_t kd[3] = {(uint64_t)(d.k_col0 + d.kv_heads * hd), (uint64_t)d.seq_len, (uint64_t)d.nseq};
+        uint64_t ks[3] = {1, (uint64_t)d.ldk, (uint64_t)d.ldk * (uint64_t)d.seq_len};
+        uint32_t kb[3] = {64, (uint32_t)bkv, 1};
+        MJV_PROPAGATE(make_tmap_bf16(&tk, d.k, 3, kd, ks, kb));
+        uint64_t vd[3] = {(uint64_t)d.seq_len, (uint64_t)hd, (uint64_t)d.nseq * (uint64_t)d.heads};
+        uint64_t vs[3] = {1, (uint64_t)d.vt_ld, (uint64_t)d.vt_plane_stride};
+        uint32_t vb[3] = {64, (uint32_t)hd, 1};
+        MJV_PROPAGATE(make_tmap_bf16(&tv, d.vt, 3, vd, vs, vb));
+        MJV_CHECK(d.heads == d.kv_heads, MJV_ERR_ARG, "attention: batched mode expects one V plane per query head");
+    }
+
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.seq_len = d.seq_len;
+    a.cu_seqlens = d.cu_seqlens;
+    a.work = reinterpret_cast<const int2*>(d.work);
+    a.heads = d.heads;
+    a.kv_group = d.heads / d.kv_heads;
+    a.q_col0 = d.q_col0;
+    a.k_col0 = d.k_col0;
+    a.out = static_cast<__nv_bfloat16*>(d.out);
+    a.ldo = (int)d.ldo;
+    a.scale_log2 = d.scale * 1.4426950408889634f;
+    a.batched = varlen ? 0 : 1;
+
+    dim3 grid;
+    if (varlen) grid = dim3((unsigned)d.n_work, (unsigned)d.heads, 1);
+    else grid = dim3((unsigned)((d.seq_len + 127) / 128), (unsigned)d.heads, (unsigned)d.nseq);
+
+    if (hd == 64) {
+        if (d.causal) return launch_attn_t<64, 128, true>(tq, tk, tv, a, grid, stream);
+        return launch_attn_t<64, 128, false>(tq, tk, tv, a, grid, stream);
+    }
+    if (d.causal) return launch_attn_t<128, 64, true>(tq, tk, tv, a, grid, stream);
+    return launch_attn_t<128, 64, false>(tq, tk, tv, a, grid, stream);
+}
+
+}  // namespace mjv
+
+extern "C" int mjv_attention(const mjv_attn_desc* desc, void* stream) {
+    if (desc == nullptr) return mjv::set_error(MJV_ERR_ARG, "mjv_attention: null desc");
+    return mjv::attention(*desc, static_cast<cudaStream_t>(stream));
+}

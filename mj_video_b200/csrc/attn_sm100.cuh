@@ -1,0 +1,335 @@
+// Fused softmax attention on tcgen05 / TMEM / TMA for sm_100a.
+//
+// Replaces K6  flash_attn_varlen_qkvpacked_func(causal=False)  modeling_intern_vit.py:72-75 / _naive_attn :210-227
+//                        K15 flash_attn_func / flash_attn_varlen_func(causal=True) modeling_internlm2.py:498-561 / eager :393-410
+//
+// One CTA = one (sequence, head, 128-query block). Per KV block j:
+//   MMA thread : S = Q·K_jᵀ (tcgen05.mma, smem x smem -> TMEM)          -> s_full
+//   softmax    : 128 threads, one query row each (TMEM lane == row): two passes over S in TMEM (row max, then
+//                p = exp2(s·c − m)), P written as bf16 into a 128B-swizzled K-major smem tile            -> p_full
+//   MMA thread : O += P·V_j (A = P from smem, B = Vᵀ tile from smem, accumulator stays in TMEM)           -> kv_empty
+// The output accumulator never leaves TMEM until the end; the running max is updated lazily (only when it grows by more
+// than 2^8), in which case O is rescaled in place with tcgen05.ld/st. tcgen05.mma executes in issue order, so the commit
+// behind S_{j} also covers P·V_{j-1}: when the softmax threads see s_full they own both P (smem) and O (TMEM).
+// MMA and softmax of one CTA alternate; two CTAs per SM (112 KB smem, 256 TMEM columns each) overlap them.
+//
+// V is consumed TRANSPOSED ([head][d][token], written that way by the QKV GEMM epilogue) so that both MMAs use the same
+// K-major operand layout as the GEMM kernel.
+#pragma once
+#include "ptx.cuh"
+
+namespace mjv {
+
+struct AttnArgs {
+    int seq_len;            // fixed sequence length when cu_seqlens == nullptr (ViT: 1025)
+    const int* cu_seqlens;  // [nseq+1] packed row offsets (LLM) or nullptr
+    const int2* work;       // [(seq, q_block)] schedule (heavy blocks first) or nullptr -> (blockIdx.z, blockIdx.x)
+    int heads;              // query heads
+    int kv_group;           // query heads per kv head
+    int q_col0, k_col0;     // first q / k column inside their tensor maps
+    __nv_bfloat16* out;     // [rows, ldo]
+    int ldo;
+    float scale_log2;       // softmax scale * log2(e)
+    int batched;            // 1: maps carry a per-sequence batch dim and rows are sequence-relative (ViT)
+};
+
+namespace attn_detail {
+constexpr int BQ = 128;
+constexpr int kThreads = 256;
+constexpr float kRescaleThreshold = 8.0f;  // log2 domain: p stays below 2^8
+
+template <int HD, int BKV>
+struct Smem {
+    static constexpr int kQBytes = BQ * HD * 2;
+    static constexpr int kKBytes = BKV * HD * 2;
+    static constexpr int kVBytes = HD * BKV * 2;
+    static constexpr int kPBytes = BQ * BKV * 2;
+    static constexpr int kStages = 2;
+    static constexpr int kQOff = 0;
+    static constexpr int kKOff = kQOff + kQBytes;
+    static constexpr int kVOff = kKOff + kStages * kKBytes;
+    static constexpr int kPOff = kVOff + kStages * kVBytes;
+    static constexpr int kBarOff = kPOff + kPBytes;
+    static constexpr int kTotal = kBarOff + 128;
+};
+}  // namespace attn_detail
+
+template <int HD, int BKV, bool CAUSAL>
+__global__ void __launch_bounds__(attn_detail::kThreads, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnArgs args) {
+    using namespace attn_detail;
+    using L = Smem<HD, BKV>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem + L::kQOff;
+    uint8_t* sK = smem + L::kKOff;
+    uint8_t* sV = smem + L::kVOff;
+    uint8_t* sP = smem + L::kPOff;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* v_full = bars + 3;    // [2]
+    uint64_t* kv_empty = bars + 5;  // [2]
+    uint64_t* s_full = bars + 7;
+    uint64_t* p_full = bars + 8;
+    uint64_t* o_done = bars + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- work item
+    int seq, qblk;
+    if (args.work != nullptr) {
+        const int2 w = args.work[blockIdx.x];
+        seq = w.x;
+        qblk = w.y;
+    } else {
+        seq = blockIdx.z;
+        qblk = blockIdx.x;
+    }
+    const int h = blockIdx.y;
+    int len, row_base;
+    if (args.cu_seqlens != nullptr) {
+        row_base = args.cu_seqlens[seq];
+        len = args.cu_seqlens[seq + 1] - row_base;
+    } else {
+        len = args.seq_len;
+        row_base = seq * len;
+    }
+    const int q0 = qblk * BQ;
+    const int kv_end = CAUSAL ? min(len, q0 + BQ) : len;
+    const int n_blocks = (kv_end + BKV - 1) / BKV;
+    const int tma_row0 = args.batched ? 0 : row_base;
+    const int tma_batch = args.batched ? seq : 0;
+    const int kvh = h / args.kv_group;
+    const int v_plane = args.batched ? seq * args.heads + h : kvh;
+
+    if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) {
+        printf("[mjv] attention: dynamic smem base not 1024-aligned\n");
+        __trap();
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmQ);
+        ptx::prefetch_tmap(&tmK);
+        ptx::prefetch_tmap(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        ptx::mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&k_full[s], 1);
+            ptx::mbar_init(&v_full[s], 1);
+            ptx::mbar_init(&kv_empty[s], 1);
+        }
+        ptx::mbar_init(s_full, 1);
+        ptx::mbar_init(p_full, 128);
+        ptx::mbar_init(o_done, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, 256);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base;        // BKV columns
+    const uint32_t tmem_O = tmem_base + 128;  // HD columns
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(q_full, L::kQBytes);
+#pragma unroll
+            for (int kd = 0; kd < HD / 64; ++kd)
+                ptx::tma_load_3d(sQ + kd * (BQ * 128), &tmQ, q_full, args.q_col0 + h * HD + kd * 64, tma_row0 + q0,
+                                 tma_batch, ptx::kEvictFirst);
+            for (int j = 0; j < n_blocks; ++j) {
+                const int st = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                ptx::mbar_wait(&kv_empty[st], ph ^ 1);
+                ptx::mbar_expect_tx(&k_full[st], L::kKBytes);
+#pragma unroll
+                for (int kd = 0; kd < HD / 64; ++kd)
+                    ptx::tma_load_3d(sK + st * L::kKBytes + kd * (BKV * 128), &tmK, &k_full[st],
+                                     args.k_col0 + kvh * HD + kd * 64, tma_row0 + j * BKV, tma_batch, ptx::kEvictLast);
+                ptx::mbar_expect_tx(&v_full[st], L::kVBytes);
+#pragma unroll
+                for (int kb = 0; kb < BKV / 64; ++kb)
+                    ptx::tma_load_3d(sV + st * L::kVBytes + kb * (HD * 128), &tmV, &v_full[st],
+                                     tma_row0 + j * BKV + kb * 64, 0, v_plane, ptx::kEvictLast);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
+            constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD);
+            const uint32_t q_addr = ptx::smem_u32(sQ);
+            const uint32_t p_addr = ptx::smem_u32(sP);
+            ptx::mbar_wait(q_full, 0);
+            for (int j = 0; j < n_blocks; ++j) {
+                const int st = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                ptx::mbar_wait(&k_full[st], ph);
+                ptx::tc_fence_after();
+                const uint32_t k_addr = ptx::smem_u32(sK + st * L::kKBytes);
+#pragma unroll
+                for (int ks = 0; ks < HD / 16; ++ks) {
+                    const uint64_t a = ptx::make_desc_sw128(q_addr + (ks >> 2) * (BQ * 128) + (ks & 3) * 32);
+                    const uint64_t b = ptx::make_desc_sw128(k_addr + (ks >> 2) * (BKV * 128) + (ks & 3) * 32);
+                    ptx::mma_bf16_ss(tmem_S, a, b, idesc_s, ks != 0 ? 1u : 0u);
+                }
+                ptx::mma_commit(s_full);
+
+                ptx::mbar_wait(p_full, j & 1);
+                ptx::mbar_wait(&v_full[st], ph);
+                ptx::tc_fence_after();
+                const uint32_t v_addr = ptx::smem_u32(sV + st * L::kVBytes);
+                const int valid = min(BKV, kv_end - j * BKV);
+                const int ksteps = (valid + 15) >> 4;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint64_t a = ptx::make_desc_sw128(p_addr + (ks >> 2) * (BQ * 128) + (ks & 3) * 32);
+                    const uint64_t b = ptx::make_desc_sw128(v_addr + (ks >> 2) * (HD * 128) + (ks & 3) * 32);
+                    ptx::mma_bf16_ss(tmem_O, a, b, idesc_o, (j | ks) != 0 ? 1u : 0u);
+                }
+                ptx::mma_commit(&kv_empty[st]);
+            }
+            ptx::mma_commit(o_done);
+        }
+    } else if (warp >= 4) {
+        // ===================================================== softmax / output (TMEM lane == query row)
+        const int qw = warp & 3;
+        const int r = qw * 32 + lane;
+        const int qrow = q0 + r;                                 // position inside the sequence
+        const bool warp_has_rows = (q0 + qw * 32) < len;         // warp-uniform
+        const uint32_t lane_sel = static_cast<uint32_t>(qw * 32) << 16;
+        float m_run = -INFINITY;
+        float l_run = 0.0f;
+        uint8_t* p_row = sP + r * 128;
+        const int swz = r & 7;
+
+        for (int j = 0; j < n_blocks; ++j) {
+            ptx::mbar_wait(s_full, j & 1);
+            ptx::tc_fence_after();
+            const int kv0 = j * BKV;
+            const int valid = min(BKV, kv_end - kv0);   // columns of this block that exist (block level)
+            const int nchunks = (valid + 31) >> 5;      // 32-column chunks the P·V MMA may read
+            // per-row column limit (exclusive, block-relative)
+            int lim = valid;
+            if (CAUSAL) lim = min(valid, qrow - kv0 + 1);
+            const bool warp_masked = CAUSAL && (kv0 > q0 + qw * 32 + 31);  // every row of this warp sees nothing here
+
+            if (warp_has_rows && !warp_masked) {
+                // ---- pass 1: block row max
+                float bm = -INFINITY;
+                for (int c = 0; c < nchunks; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_x32(tmem_S + lane_sel + c * 32, v);
+                    ptx::tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float t = __uint_as_float(v[i]) * args.scale_log2;
+                        bm = fmaxf(bm, (c * 32 + i < lim) ? t : -INFINITY);
+                    }
+                }
+                // ---- lazy rescale of the TMEM accumulator
+                float alpha = 1.0f;
+                bool need = false;
+                if (j == 0) {
+                    m_run = bm;
+                } else if (bm > m_run + kRescaleThreshold) {
+                    alpha = ptx::ex2_approx(m_run - bm);
+                    m_run = bm;
+                    need = true;
+                }
+                if (__any_sync(0xffffffffu, need)) {
+                    l_run *= alpha;
+#pragma unroll 1
+                    for (int c = 0; c < HD / 32; ++c) {
+                        uint32_t o[32];
+                        ptx::tmem_ld_x32(tmem_O + lane_sel + c * 32, o);
+                        ptx::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        ptx::tmem_st_x32(tmem_O + lane_sel + c * 32, o);
+                    }
+                    ptx::tmem_wait_st();
+                }
+                // ---- pass 2: p = exp2(s*c - m), row sum, bf16 P tile (128B swizzle: 16B chunk index ^= row & 7)
+                float psum = 0.0f;
+                for (int c = 0; c < nchunks; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_x32(tmem_S + lane_sel + c * 32, v);
+                    ptx::tmem_wait_ld();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i]), args.scale_log2, -m_run));
+                        float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), args.scale_log2, -m_run));
+                        p0 = (c * 32 + 2 * i < lim) ? p0 : 0.0f;
+                        p1 = (c * 32 + 2 * i + 1 < lim) ? p1 : 0.0f;
+                        psum += p0 + p1;
+                        pk[i] = ptx::pack_bf16x2(p0, p1);
+                    }
+                    uint8_t* blk = p_row + (c >> 1) * (BQ * 128);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int chunk16 = ((c & 1) * 4 + g) ^ swz;
+                        *reinterpret_cast<uint4*>(blk + chunk16 * 16) =
+                            make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                    }
+                }
+                l_run += psum;
+            } else if (warp_has_rows) {
+                // rows exist but see no column of this block: P rows must be exact zeros
+                for (int c = 0; c < nchunks; ++c) {
+                    uint8_t* blk = p_row + (c >> 1) * (BQ * 128);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int chunk16 = ((c & 1) * 4 + g) ^ swz;
+                        *reinterpret_cast<uint4*>(blk + chunk16 * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(p_full);
+        }
+
+        // ---- epilogue: O / l -> bf16
+        ptx::mbar_wait(o_done, 0);
+        ptx::tc_fence_after();
+        if (warp_has_rows) {
+            const float inv = 1.0f / l_run;
+            __nv_bfloat16* dst = args.out + static_cast<long long>(row_base + qrow) * args.ldo + h * HD;
+#pragma unroll 1
+            for (int c = 0; c < HD / 32; ++c) {
+                uint32_t o[32];
+                ptx::tmem_ld_x32(tmem_O + lane_sel + c * 32, o);
+                ptx::tmem_wait_ld();
+                if (qrow < len) {
+                    uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        d4[g] = make_uint4(
+                            ptx::pack_bf16x2(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv),
+                            ptx::pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv),
+                            ptx::pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv),
+                            ptx::pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv));
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 256);
+    }
+}
+
+}  // namespace mjv

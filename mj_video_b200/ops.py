@@ -55,3 +55,33 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None, *, e
     d.vt_stride_head, d.vt_ld, d.seq, d.heads = vt_stride_head, vt_ld, seq, heads
     _lib.check(lib.mjv_gemm_bf16(C.byref(d), _lib.current_stream()))
     return out
+
+
+def attention(q, k, vt, out, *, head_dim, heads, kv_heads, causal, scale, q_col0=0, k_col0=0, nseq=0, seq_len=0,
+              cu_seqlens=None, work=None, vt_ld=None, vt_plane_stride=None):
+    """Fused attention. Batched mode: q/k are [nseq*seq_len, ld] and vt is [nseq*heads, head_dim, vt_ld].
+    Varlen mode: packed rows with device int32 cu_seqlens[nseq+1] and work[(seq, q_block)] pairs; vt is
+    [kv_heads, head_dim, vt_ld]."""
+    lib = _lib.load()
+    d = _lib.AttnDesc()
+    d.q, d.k, d.vt, d.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
+    d.ldq, d.ldk, d.ldo = q.stride(0), k.stride(0), out.stride(0)
+    d.vt_ld = vt_ld if vt_ld is not None else vt.stride(-2)
+    d.vt_plane_stride = vt_plane_stride if vt_plane_stride is not None else vt.stride(0)
+    d.total_rows = q.shape[0]
+    d.head_dim, d.heads, d.kv_heads = head_dim, heads, kv_heads
+    d.q_col0, d.k_col0, d.causal = q_col0, k_col0, int(causal)
+    d.nseq, d.seq_len = nseq, seq_len
+    d.cu_seqlens = _lib.ptr(cu_seqlens)
+    d.work = _lib.ptr(work)
+    d.n_work = 0 if work is None else work.shape[0]
+    d.scale = scale
+    _lib.check(lib.mjv_attention(C.byref(d), _lib.current_stream()))
+    return out
+
+
+def causal_work_list(lengths, block_q: int = 128):
+    """(sequence, q_block) pairs, heaviest (largest q_block) first so long causal rows start early."""
+    items = [(s, b) for s, n in enumerate(lengths) for b in range((n + block_q - 1) // block_q)]
+    items.sort(key=lambda t: -t[1])
+    return torch.tensor(items, dtype=torch.int32)

@@ -77,6 +77,7 @@ typedef struct mjv_gemm_desc {
     const float* rope_sin;
     const int32_t* row_pos; /* QKV_LLM: position id of each row                      */
     const int32_t* row_map; /* SCATTER: destination row of each m                    */
+    const int32_t* row_vt;  /* QKV_LLM: V^T column of each row (NULL = row index)    */
     const void* pos_emb;  /* PATCH: [seq+1, N] bf16                                  */
     int32_t n_q_cols, n_k_cols;
     int64_t vt_stride_head;
@@ -111,6 +112,9 @@ typedef struct mjv_attn_desc {
     int32_t nseq, seq_len;
     const int32_t* cu_seqlens; /* device [nseq+1] or NULL                                                 */
     const int32_t* work;       /* device int32[2*n_work] (seq, q_block) pairs or NULL                     */
+    const int32_t* vt_starts;  /* varlen: device [nseq] first V^T column of each sequence (multiple of 8: TMA
+                                  needs a 16-byte aligned innermost coordinate) or NULL (= cu_seqlens)      */
+    int64_t vt_cols;           /* varlen: number of V^T columns in use (<= vt_ld); 0 = total_rows         */
     int32_t n_work;
     float scale;          /* softmax scale (1/sqrt(head_dim))                                             */
 } mjv_attn_desc;

@@ -27,7 +27,7 @@ class GemmDesc(C.Structure):
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64), ("scale", C.c_void_p),
         ("out_k", C.c_void_p), ("out_vt", C.c_void_p),
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
-        ("row_pos", C.c_void_p), ("row_map", C.c_void_p), ("pos_emb", C.c_void_p),
+        ("row_pos", C.c_void_p), ("row_map", C.c_void_p), ("row_vt", C.c_void_p), ("pos_emb", C.c_void_p),
         ("n_q_cols", C.c_int32), ("n_k_cols", C.c_int32),
         ("vt_stride_head", C.c_int64), ("vt_ld", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32),
     ]
@@ -41,7 +41,8 @@ class AttnDesc(C.Structure):
         ("head_dim", C.c_int32), ("heads", C.c_int32), ("kv_heads", C.c_int32),
         ("q_col0", C.c_int32), ("k_col0", C.c_int32), ("causal", C.c_int32),
         ("nseq", C.c_int32), ("seq_len", C.c_int32),
-        ("cu_seqlens", C.c_void_p), ("work", C.c_void_p), ("n_work", C.c_int32), ("scale", C.c_float),
+        ("cu_seqlens", C.c_void_p), ("work", C.c_void_p), ("vt_starts", C.c_void_p), ("vt_cols", C.c_int64),
+        ("n_work", C.c_int32), ("scale", C.c_float),
     ]
 
 

@@ -41,7 +41,7 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
         uint64_t ks[3] = {1, (uint64_t)d.ldk, (uint64_t)d.ldk * (uint64_t)d.total_rows};
         uint32_t kb[3] = {64, (uint32_t)bkv, 1};
         MJV_PROPAGATE(make_tmap_bf16(&tk, d.k, 3, kd, ks, kb));
-        uint64_t vd[3] = {(uint64_t)d.total_rows, (uint64_t)hd, (uint64_t)d.kv_heads};
+        uint64_t vd[3] = {(uint64_t)(d.vt_cols > 0 ? d.vt_cols : d.total_rows), (uint64_t)hd, (uint64_t)d.kv_heads};
         uint64_t vs[3] = {1, (uint64_t)d.vt_ld, (uint64_t)d.vt_plane_stride};
         uint32_t vb[3] = {64, (uint32_t)hd, 1};
         MJV_PROPAGATE(make_tmap_bf16(&tv, d.vt, 3, vd, vs, vb));
@@ -66,6 +66,7 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     a.seq_len = d.seq_len;
     a.cu_seqlens = d.cu_seqlens;
     a.work = reinterpret_cast<const int2*>(d.work);
+    a.vt_starts = d.vt_starts;
     a.heads = d.heads;
     a.kv_group = d.heads / d.kv_heads;
     a.q_col0 = d.q_col0;

@@ -24,6 +24,7 @@ struct AttnArgs {
     int seq_len;            // fixed sequence length when cu_seqlens == nullptr (ViT: 1025)
     const int* cu_seqlens;  // [nseq+1] packed row offsets (LLM) or nullptr
     const int2* work;       // [(seq, q_block)] schedule (heavy blocks first) or nullptr -> (blockIdx.z, blockIdx.x)
+    const int* vt_starts;   // varlen: first V^T column of each sequence (8-aligned) or nullptr (= cu_seqlens)
     int heads;              // query heads
     int kv_group;           // query heads per kv head
     int q_col0, k_col0;     // first q / k column inside their tensor maps
@@ -104,6 +105,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int tma_batch = args.batched ? seq : 0;
     const int kvh = h / args.kv_group;
     const int v_plane = args.batched ? seq * args.heads + h : kvh;
+    const int v_col0 = args.batched ? 0 : (args.vt_starts != nullptr ? args.vt_starts[seq] : row_base);
 
     if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) {
         printf("[mjv] attention: dynamic smem base not 1024-aligned\n");
@@ -158,7 +160,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
                 for (int kb = 0; kb < BKV / 64; ++kb)
                     ptx::tma_load_3d(sV + st * L::kVBytes + kb * (HD * 128), &tmV, &v_full[st],
-                                     tma_row0 + j * BKV + kb * 64, 0, v_plane, ptx::kEvictLast);
+                                     v_col0 + j * BKV + kb * 64, 0, v_plane, ptx::kEvictLast);
             }
         }
     } else if (warp == 1) {

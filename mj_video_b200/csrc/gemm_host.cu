@@ -80,6 +80,7 @@ int gemm_bf16(const mjv_gemm_desc& d, cudaStream_t stream) {
     a.rope_sin = d.rope_sin;
     a.row_pos = d.row_pos;
     a.row_map = d.row_map;
+    a.row_vt = d.row_vt;
     a.pos = static_cast<const __nv_bfloat16*>(d.pos_emb);
     a.n_q_cols = d.n_q_cols;
     a.n_k_cols = d.n_k_cols;

@@ -43,6 +43,7 @@ struct GemmArgs {
     const float* rope_sin;     // [max_pos, 64]
     const int* row_pos;        // QKV_LLM: position id per packed token row
     const int* row_map;        // SCATTER: destination row per m
+    const int* row_vt;         // QKV_LLM: V^T column per packed token row (sequence starts 8-aligned for TMA)
     const __nv_bfloat16* pos;  // PATCH: position embedding [P+1, N]
     int n_q_cols;              // QKV: number of q columns
     int n_k_cols;              // QKV: number of k columns
@@ -335,7 +336,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     } else {
                         // V head: transposed store, V^T[head][d][token]
                         const int vcol = n - args.n_q_cols - args.n_k_cols;  // head*128
-                        __nv_bfloat16* dst = args.out_vt + static_cast<long long>(vcol >> 7) * args.vt_stride_head + row;
+                        const int vtc = (row_ok && args.row_vt != nullptr) ? args.row_vt[row] : row;
+                        __nv_bfloat16* dst = args.out_vt + static_cast<long long>(vcol >> 7) * args.vt_stride_head + vtc;
 #pragma unroll 1
                         for (int c = 0; c < 128; c += 32) {
                             uint32_t v[32];

@@ -24,7 +24,7 @@ def _bf16(t: torch.Tensor | None, name: str) -> torch.Tensor | None:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None, *, epilogue: int = EPI_STORE,
          bias=None, residual=None, scale=None, block_n: int = 0, out_k=None, out_vt=None, rope_cos=None,
-         rope_sin=None, row_pos=None, row_map=None, pos_emb=None, n_q_cols: int = 0, n_k_cols: int = 0,
+         rope_sin=None, row_pos=None, row_map=None, row_vt=None, pos_emb=None, n_q_cols: int = 0, n_k_cols: int = 0,
          vt_stride_head: int = 0, vt_ld: int = 0, seq: int = 0, heads: int = 0, ldo: int | None = None,
          K: int | None = None) -> torch.Tensor:
     """D = A · Wᵀ with a fused epilogue (tcgen05 / TMEM / TMA). a: [M, K] bf16, w: [N, K] bf16 (nn.Linear layout)."""
@@ -51,6 +51,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None, *, e
     d.out_k, d.out_vt = _lib.ptr(out_k), _lib.ptr(out_vt)
     d.rope_cos, d.rope_sin = _lib.ptr(rope_cos), _lib.ptr(rope_sin)
     d.row_pos, d.row_map, d.pos_emb = _lib.ptr(row_pos), _lib.ptr(row_map), _lib.ptr(pos_emb)
+    d.row_vt = _lib.ptr(row_vt)
     d.n_q_cols, d.n_k_cols = n_q_cols, n_k_cols
     d.vt_stride_head, d.vt_ld, d.seq, d.heads = vt_stride_head, vt_ld, seq, heads
     _lib.check(lib.mjv_gemm_bf16(C.byref(d), _lib.current_stream()))
@@ -58,7 +59,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None, *, e
 
 
 def attention(q, k, vt, out, *, head_dim, heads, kv_heads, causal, scale, q_col0=0, k_col0=0, nseq=0, seq_len=0,
-              cu_seqlens=None, work=None, vt_ld=None, vt_plane_stride=None):
+              cu_seqlens=None, work=None, vt_ld=None, vt_plane_stride=None, vt_starts=None, vt_cols=0):
     """Fused attention. Batched mode: q/k are [nseq*seq_len, ld] and vt is [nseq*heads, head_dim, vt_ld].
     Varlen mode: packed rows with device int32 cu_seqlens[nseq+1] and work[(seq, q_block)] pairs; vt is
     [kv_heads, head_dim, vt_ld]."""
@@ -74,6 +75,8 @@ def attention(q, k, vt, out, *, head_dim, heads, kv_heads, causal, scale, q_col0
     d.nseq, d.seq_len = nseq, seq_len
     d.cu_seqlens = _lib.ptr(cu_seqlens)
     d.work = _lib.ptr(work)
+    d.vt_starts = _lib.ptr(vt_starts)
+    d.vt_cols = vt_cols
     d.n_work = 0 if work is None else work.shape[0]
     d.scale = scale
     _lib.check(lib.mjv_attention(C.byref(d), _lib.current_stream()))
@@ -85,3 +88,13 @@ def causal_work_list(lengths, block_q: int = 128):
     items = [(s, b) for s, n in enumerate(lengths) for b in range((n + block_q - 1) // block_q)]
     items.sort(key=lambda t: -t[1])
     return torch.tensor(items, dtype=torch.int32)
+
+
+def vt_layout(lengths, align: int = 8):
+    """Column layout of the transposed-V buffer in varlen mode: each sequence starts at a multiple of `align`
+    columns (TMA needs a 16-byte aligned innermost coordinate). Returns (starts, total_cols)."""
+    starts, off = [], 0
+    for n in lengths:
+        starts.append(off)
+        off += (n + align - 1) // align * align
+    return starts, off

@@ -74,15 +74,19 @@ if ok_all:
         q = torch.randn(tot, H, 128, device=dev).bfloat16()
         k = torch.randn(tot, Hkv, 128, device=dev).bfloat16()
         v = torch.randn(tot, Hkv, 128, device=dev).bfloat16()
-        tot_pad = (tot + 7) // 8 * 8
+        starts, tot_pad = ops.vt_layout(lens)
         vt = torch.zeros(Hkv, 128, tot_pad, device=dev, dtype=torch.bfloat16)
-        vt[:, :, :tot] = v.permute(1, 2, 0)
+        o = 0
+        for st, n in zip(starts, lens):
+            vt[:, :, st:st + n] = v[o:o + n].permute(1, 2, 0)
+            o += n
+        vts = torch.tensor(starts, dtype=torch.int32, device=dev)
         cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
         work = ops.causal_work_list(lens).to(dev)
         out = torch.zeros(tot, H * 128, device=dev, dtype=torch.bfloat16)
         try:
             ops.attention(q.reshape(tot, -1), k.reshape(tot, -1), vt, out, head_dim=128, heads=H, kv_heads=Hkv,
-                          causal=True, scale=1 / math.sqrt(128), cu_seqlens=cu, work=work)
+                          causal=True, scale=1 / math.sqrt(128), cu_seqlens=cu, work=work, vt_starts=vts, vt_cols=tot_pad)
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
             print("EXCEPTION", e)
@@ -167,13 +171,14 @@ if ok_all:
     tot = sum(lens)
     q = torch.randn(tot, 16 * 128, device=dev).bfloat16()
     k = torch.randn(tot, 8 * 128, device=dev).bfloat16()
-    tot_pad = (tot + 7) // 8 * 8
+    starts, tot_pad = ops.vt_layout(lens)
     vt = torch.randn(8, 128, tot_pad, device=dev).bfloat16()
+    vts = torch.tensor(starts, dtype=torch.int32, device=dev)
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
     work = ops.causal_work_list(lens).to(dev)
     out = torch.zeros(tot, 2048, device=dev, dtype=torch.bfloat16)
     ms = timeit(lambda: ops.attention(q, k, vt, out, head_dim=128, heads=16, kv_heads=8, causal=True,
-                                      scale=1 / math.sqrt(128), cu_seqlens=cu, work=work))
+                                      scale=1 / math.sqrt(128), cu_seqlens=cu, work=work, vt_starts=vts, vt_cols=tot_pad))
     fl = sum(4.0 * 16 * 128 * n * (n + 1) / 2 for n in lens)
     print(f"[perf] llm attention 32x2187: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s (causal-exact flops)")
 

@@ -121,6 +121,121 @@ typedef struct mjv_attn_desc {
 
 int mjv_attention(const mjv_attn_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Row-wise primitives (test hooks; the engine calls the same kernels internally)
+ *   mjv_layernorm               nn.LayerNorm            modeling_intern_vit.py:291,293
+ *   mjv_pixel_shuffle_layernorm pixel_shuffle('v2') + mlp1[0]  modeling_internvl_chat.py:228-262,136
+ *   mjv_rmsnorm                 InternLM2RMSNorm        modeling_internlm2.py:138-143 (row_idx gathers source rows)
+ *   mjv_embed_tokens            tok_embeddings lookup   modeling_internvl_chat.py:163 (IMG_CONTEXT rows skipped)
+ *   mjv_im2col_patches          nn.Conv2d(3,C,14,14) operand layout  modeling_intern_vit.py:164
+ * ---------------------------------------------------------------------------------------------------------- */
+int mjv_layernorm(const void* x, const void* w, const void* b, void* out, int64_t rows, int32_t C, float eps,
+                  void* stream);
+int mjv_pixel_shuffle_layernorm(const void* vit_hidden, const void* w, const void* b, void* out, int32_t tiles,
+                                int32_t seq, int32_t c_vit, float eps, void* stream);
+int mjv_rmsnorm(const void* x, const void* w, void* out, int64_t rows, int32_t C, float eps, const int32_t* row_idx,
+                void* stream);
+int mjv_embed_tokens(const int32_t* ids, const void* table, void* out, int64_t rows, int32_t C, int32_t img_ctx_id,
+                     int32_t vocab, void* stream);
+int mjv_im2col_patches(const void* px, int32_t px_dtype, void* out, int32_t T, int32_t img, int32_t ps, int32_t Kpad,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Frame path: uint8 [n_frames, H, W, 3] frames (device) -> normalised CHW tiles [n_frames*tiles_per_frame,3,S,S].
+ * Replaces the per-frame body of load_video (data_processor/data.py:158-179): dynamic_preprocess (data.py:81-117,
+ * PIL bicubic resize + row-major crops + thumbnail) and build_transform (data.py:56-64). Bit-exact with Pillow.
+ * `out` NULL = query tiles_per_frame only. `scratch` (uint8, >= n_frames*H*max(S*gi,S)*3 bytes) is needed only when a
+ * resize happens. mjv_choose_grid / mjv_bicubic_coeffs are pure host helpers (usable without a GPU).
+ * ---------------------------------------------------------------------------------------------------------- */
+int mjv_preprocess_frames(const void* frames_u8, int32_t n_frames, int32_t height, int32_t width, int32_t image_size,
+                          int32_t max_num, int32_t use_thumbnail, void* out, int32_t out_dtype, void* scratch,
+                          int64_t scratch_bytes, int32_t* tiles_per_frame, void* stream);
+int mjv_choose_grid(int32_t width, int32_t height, int32_t min_num, int32_t max_num, int32_t image_size, int32_t* gi,
+                    int32_t* gj);
+int mjv_bicubic_coeffs(int32_t in_size, int32_t out_size, int32_t* ksize, int32_t* bounds, int32_t* kk,
+                       int64_t kk_capacity);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Model handle: one per (device, model). Replaces InternVLChatRewardModeling.__init__ / load_state_dict
+ * (moe_reward.py:138-181; eval_genai_mjvideo.py:91-115) and .forward (moe_reward.py:183-297).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct mjv_handle mjv_handle;
+
+enum { MJV_LLM_INTERNLM2 = 0, MJV_LLM_LLAMA = 1 };
+
+typedef struct mjv_config {
+    int32_t image_size, patch_size;
+    int32_t vit_hidden, vit_heads, vit_mlp, vit_layers;
+    float vit_eps;
+    int32_t llm_arch;
+    int32_t llm_hidden, llm_inter, llm_layers, llm_heads, llm_kv_heads, vocab;
+    float rms_eps;
+    int32_t max_pos;
+    float mlp1_eps;
+    int32_t num_objectives, num_aspects, gating_hidden, gating_n_hidden;
+    float gating_temperature;
+    int32_t group_offsets[33]; /* aspect2criteria in dict order: items of aspect a are                      */
+    int32_t group_items[32];   /*   group_items[group_offsets[a] .. group_offsets[a+1])                     */
+} mjv_config;
+
+int mjv_create(const mjv_config* cfg, mjv_handle** out);
+void mjv_destroy(mjv_handle* h);
+/* Copy + re-pack one tensor of the reference state dict (SURVEY §A.2 key names; also "rope.cos"/"rope.sin"
+ * [max_pos, head_dim/2] fp32 tables built by the host shim exactly as InternLM2RotaryEmbedding does).
+ * `data` may be host or device memory. Unused keys (e.g. language_model.output.weight) are accepted and dropped. */
+int mjv_load_weight(mjv_handle* h, const char* key, const void* data, const int64_t* shape, int32_t ndim,
+                    int32_t dtype);
+/* Check that every tensor the forward needs is present; returns MJV_ERR_STATE and names the first missing key. */
+int mjv_finalize_weights(mjv_handle* h);
+int64_t mjv_workspace_bytes(const mjv_handle* h, int32_t n_rows, int32_t n_tiles, int64_t n_tokens);
+
+/* One batch, already indexed by the host shim from the CPU copy of input_ids (no device->host sync on the path):
+ * rows are PACKED (padding removed): sequence b owns packed token rows [cu_seqlens[b], cu_seqlens[b+1]). */
+typedef struct mjv_batch {
+    int32_t n_rows;            /* B samples                                                                  */
+    int32_t n_tiles;           /* T tiles in pixel_values                                                     */
+    int32_t n_img_tokens;      /* number of <IMG_CONTEXT> tokens that receive a projector row (<= T*tokens)   */
+    int32_t n_work;            /* entries of `work`                                                           */
+    int32_t img_context_token_id; /* rows holding this id are written by the projector, not the embedding table */
+    int64_t n_tokens;          /* M = sum of real sequence lengths                                            */
+    int64_t vt_cols;           /* columns of the transposed-V buffer (sum of 8-aligned lengths)               */
+    const void* pixel_values;  /* device [T,3,S,S]                                                            */
+    int32_t pixel_dtype;       /* MJV_DTYPE_BF16 or MJV_DTYPE_F32                                             */
+    const int32_t* token_ids;  /* device [M] packed token ids                                                 */
+    const int32_t* row_pos;    /* device [M] position inside the sequence                                     */
+    const int32_t* row_vt;     /* device [M] transposed-V column                                              */
+    const int32_t* img_rows;   /* device [n_img_tokens] packed row of the i-th <IMG_CONTEXT> token (row-major)*/
+    const int32_t* cu_seqlens; /* device [B+1]                                                                */
+    const int32_t* vt_starts;  /* device [B]                                                                  */
+    const int32_t* work;       /* device [2*n_work] (sequence, 128-row query block), heavy first              */
+    const int32_t* gather_rows;/* device [2B]: packed rows of the last real token (moe_reward.py:226-228) then
+                                  of the gating token (find_token_for_gating, moe_reward.py:50-57)            */
+} mjv_batch;
+
+typedef struct mjv_outputs {
+    float* scores;   /* device [B, 34]: rewards(28) | aspect_scores(5) | score(1)  (NO | NA | 1 in general)   */
+    float* extras;   /* device [B, NO+NA+NO+1]: criteria_gating_output | aspect_gating_output |
+                        aspect_weights | weighted_scores                                                      */
+    void* hidden_state;      /* device bf16 [B, D] (moe_reward.py:236-237)                                    */
+    void* prompt_embedding;  /* device bf16 [B, D] (moe_reward.py:243)                                        */
+} mjv_outputs;
+
+/* stage entry points (each separately testable / profilable); all enqueue on `stream` and return immediately */
+int mjv_vit_forward(mjv_handle* h, const void* pixel_values, int32_t pixel_dtype, int32_t n_tiles, void* vit_hidden,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+int mjv_project_and_splice(mjv_handle* h, const void* vit_hidden, const mjv_batch* batch, void* embeds,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+int mjv_llm_prefill(mjv_handle* h, void* embeds_inout, const mjv_batch* batch, void* gathered_2b,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+int mjv_reward_head(mjv_handle* h, const void* gathered_2b, int32_t n_rows, const mjv_outputs* out, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+/* the whole forward: ViT -> projector -> splice -> LLM prefill -> head */
+int mjv_score_forward(mjv_handle* h, const mjv_batch* batch, const mjv_outputs* out, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+long long mjv_launch_count(void);
+void mjv_reset_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,37 @@ class AttnDesc(C.Structure):
     ]
 
 
+class Config(C.Structure):
+    _fields_ = [
+        ("image_size", C.c_int32), ("patch_size", C.c_int32),
+        ("vit_hidden", C.c_int32), ("vit_heads", C.c_int32), ("vit_mlp", C.c_int32), ("vit_layers", C.c_int32),
+        ("vit_eps", C.c_float),
+        ("llm_arch", C.c_int32),
+        ("llm_hidden", C.c_int32), ("llm_inter", C.c_int32), ("llm_layers", C.c_int32), ("llm_heads", C.c_int32),
+        ("llm_kv_heads", C.c_int32), ("vocab", C.c_int32),
+        ("rms_eps", C.c_float), ("max_pos", C.c_int32), ("mlp1_eps", C.c_float),
+        ("num_objectives", C.c_int32), ("num_aspects", C.c_int32), ("gating_hidden", C.c_int32),
+        ("gating_n_hidden", C.c_int32), ("gating_temperature", C.c_float),
+        ("group_offsets", C.c_int32 * 33), ("group_items", C.c_int32 * 32),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("n_rows", C.c_int32), ("n_tiles", C.c_int32), ("n_img_tokens", C.c_int32), ("n_work", C.c_int32),
+        ("img_context_token_id", C.c_int32),
+        ("n_tokens", C.c_int64), ("vt_cols", C.c_int64),
+        ("pixel_values", C.c_void_p), ("pixel_dtype", C.c_int32),
+        ("token_ids", C.c_void_p), ("row_pos", C.c_void_p), ("row_vt", C.c_void_p), ("img_rows", C.c_void_p),
+        ("cu_seqlens", C.c_void_p), ("vt_starts", C.c_void_p), ("work", C.c_void_p), ("gather_rows", C.c_void_p),
+    ]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("scores", C.c_void_p), ("extras", C.c_void_p), ("hidden_state", C.c_void_p),
+                ("prompt_embedding", C.c_void_p)]
+
+
 def lib_path() -> Path:
     return _LIB_PATH
 
@@ -68,6 +99,32 @@ def load() -> C.CDLL:
     lib.mjv_gemm_bf16.restype = C.c_int
     lib.mjv_attention.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
     lib.mjv_attention.restype = C.c_int
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.mjv_layernorm.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp]
+    lib.mjv_pixel_shuffle_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp]
+    lib.mjv_rmsnorm.argtypes = [vp, vp, vp, i64, i32, f32, vp, vp]
+    lib.mjv_embed_tokens.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
+    lib.mjv_im2col_patches.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp]
+    lib.mjv_preprocess_frames.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, i32, vp, i64, C.POINTER(i32), vp]
+    lib.mjv_choose_grid.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    lib.mjv_bicubic_coeffs.argtypes = [i32, i32, C.POINTER(i32), vp, vp, i64]
+    lib.mjv_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.mjv_destroy.argtypes = [vp]
+    lib.mjv_destroy.restype = None
+    lib.mjv_load_weight.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32, i32]
+    lib.mjv_finalize_weights.argtypes = [vp]
+    lib.mjv_workspace_bytes.argtypes = [vp, i32, i32, i64]
+    lib.mjv_workspace_bytes.restype = i64
+    lib.mjv_vit_forward.argtypes = [vp, vp, i32, i32, vp, vp, i64, vp]
+    lib.mjv_project_and_splice.argtypes = [vp, vp, C.POINTER(Batch), vp, vp, i64, vp]
+    lib.mjv_llm_prefill.argtypes = [vp, vp, C.POINTER(Batch), vp, vp, i64, vp]
+    lib.mjv_reward_head.argtypes = [vp, vp, i32, C.POINTER(Outputs), vp, i64, vp]
+    lib.mjv_score_forward.argtypes = [vp, C.POINTER(Batch), C.POINTER(Outputs), vp, i64, vp]
+    for name in ("mjv_layernorm", "mjv_pixel_shuffle_layernorm", "mjv_rmsnorm", "mjv_embed_tokens",
+                 "mjv_im2col_patches", "mjv_preprocess_frames", "mjv_choose_grid", "mjv_bicubic_coeffs", "mjv_create",
+                 "mjv_load_weight", "mjv_finalize_weights", "mjv_vit_forward", "mjv_project_and_splice",
+                 "mjv_llm_prefill", "mjv_reward_head", "mjv_score_forward"):
+        getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
 

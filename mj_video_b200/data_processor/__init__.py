@@ -1,0 +1,2 @@
+"""Mirror of the reference's `scripts/data_processor/__init__.py` exports that lie on the scoring path."""
+from .data import (find_closest_aspect_ratio, get_index, load_video, open_video, preprocess_frames)  # noqa: F401

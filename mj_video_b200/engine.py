@@ -1,0 +1,283 @@
+"""Host-side engine: owns the C handle, feeds it the reference state dict, turns a right-padded batch of `input_ids`
+into the packed index metadata the kernels need (on the host, from the CPU copy of the ids — the reference's device
+syncs `nonzero`, `ids.tolist()`, `0 in attention_mask` disappear), and launches `mjv_score_forward`.
+
+Index semantics are the reference's:
+  last token  : ((ids == pad).int().argmax(-1) - 1) % N          moe_reward.py:226-228
+  gating token: start of the LAST occurrence of token_pattern     moe_reward.py:45-57  (ValueError if absent)
+  image rows  : row-major positions of <IMG_CONTEXT> receive the projector rows in order
+                                                                 modeling_internvl_chat.py:176-188
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import warnings
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+TOKEN_PATTERN = [92542, 92543, 525, 11353, 364]  # '<|im_end|><|im_start|>assistant\n' (moe_reward.py:48)
+
+
+def find_token_for_gating(lst, token_pattern=None) -> int:
+    """Index of the last occurrence of `token_pattern` in `lst` (moe_reward.py:50-57)."""
+    pat = TOKEN_PATTERN if token_pattern is None else list(token_pattern)
+    n = len(pat)
+    arr = np.asarray(lst)
+    if arr.size >= n:
+        hit = np.ones(arr.size - n + 1, dtype=bool)
+        for i, p in enumerate(pat):
+            hit &= arr[i:arr.size - n + 1 + i] == p
+        idx = np.flatnonzero(hit)
+        if idx.size:
+            return int(idx[-1])
+    raise ValueError("Token pattern not found in the list.")
+
+
+@dataclass
+class EngineDims:
+    image_size: int
+    patch_size: int
+    vit_hidden: int
+    vit_heads: int
+    vit_mlp: int
+    vit_layers: int
+    vit_eps: float
+    llm_arch: int
+    llm_hidden: int
+    llm_inter: int
+    llm_layers: int
+    llm_heads: int
+    llm_kv_heads: int
+    vocab: int
+    rms_eps: float
+    rope_theta: float
+    max_pos: int
+    num_objectives: int
+    num_aspects: int
+    gating_hidden: int
+    gating_n_hidden: int
+    gating_temperature: float
+    aspect2criteria: dict
+    downsample_ratio: float = 0.5
+    mlp1_eps: float = 1e-5
+
+    @staticmethod
+    def from_synth(d) -> "EngineDims":
+        """From mj_video_b200.synth.ModelDims."""
+        return EngineDims(
+            image_size=d.image_size, patch_size=d.patch_size, vit_hidden=d.vit_hidden, vit_heads=d.vit_heads,
+            vit_mlp=d.vit_mlp, vit_layers=d.vit_layers, vit_eps=d.vit_eps, llm_arch=0, llm_hidden=d.llm_hidden,
+            llm_inter=d.llm_inter, llm_layers=d.llm_layers, llm_heads=d.llm_heads, llm_kv_heads=d.llm_kv_heads,
+            vocab=d.vocab, rms_eps=d.rms_eps, rope_theta=d.rope_theta, max_pos=d.max_pos,
+            num_objectives=d.num_objectives, num_aspects=d.num_aspects, gating_hidden=d.gating_hidden,
+            gating_n_hidden=d.gating_n_hidden, gating_temperature=d.gating_temperature,
+            aspect2criteria={k: list(v) for k, v in d.aspect2criteria.items()}, downsample_ratio=d.downsample_ratio)
+
+    @property
+    def vit_seq(self) -> int:
+        return (self.image_size // self.patch_size) ** 2 + 1
+
+    @property
+    def tokens_per_tile(self) -> int:
+        return int((self.image_size // self.patch_size) ** 2 * self.downsample_ratio ** 2)
+
+
+_DTYPES = {torch.float32: _lib.MJV_DTYPE_F32, torch.bfloat16: _lib.MJV_DTYPE_BF16, torch.float16: _lib.MJV_DTYPE_F16}
+
+
+class Engine:
+    """One model on one CUDA device. Not thread-safe (like the reference nn.Module)."""
+
+    def __init__(self, dims: EngineDims, device: torch.device | str = "cuda"):
+        self.lib = _lib.load()
+        self.dims = dims
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.MjvError("mj_video_b200 runs on CUDA devices only (no CPU fallback)")
+        if dims.downsample_ratio != 0.5:
+            raise _lib.MjvError("only downsample_ratio=0.5 (pixel-shuffle 2x2) is implemented")
+        cfg = _lib.Config()
+        for f in ("image_size", "patch_size", "vit_hidden", "vit_heads", "vit_mlp", "vit_layers", "vit_eps", "llm_arch",
+                  "llm_hidden", "llm_inter", "llm_layers", "llm_heads", "llm_kv_heads", "vocab", "rms_eps", "max_pos",
+                  "mlp1_eps", "num_objectives", "num_aspects", "gating_hidden", "gating_n_hidden",
+                  "gating_temperature"):
+            setattr(cfg, f, getattr(dims, f))
+        off = 0
+        for a, (_, items) in enumerate(dims.aspect2criteria.items()):
+            cfg.group_offsets[a] = off
+            for it in items:
+                cfg.group_items[off] = int(it)
+                off += 1
+        for a in range(len(dims.aspect2criteria), 33):
+            cfg.group_offsets[a] = off
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mjv_create(C.byref(cfg), C.byref(self._handle)))
+        self._workspace: torch.Tensor | None = None
+        self._finalized = False
+        self._load_rope()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                self.lib.mjv_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # -------------------------------------------------------------------------------------------- weights
+    def _load_rope(self):
+        """cos/sin tables exactly as InternLM2RotaryEmbedding builds them (modeling_internlm2.py:147-170): fp32 on the
+        host; in bf16 models the buffers are cast with the model, so the table holds bf16-rounded values."""
+        d = self.dims
+        hd = d.llm_hidden // d.llm_heads
+        inv_freq = 1.0 / (d.rope_theta ** (torch.arange(0, hd, 2).float() / hd))
+        t = torch.arange(d.max_pos, dtype=inv_freq.dtype)
+        freqs = torch.einsum("i,j->ij", t, inv_freq)
+        cos = freqs.cos().to(torch.bfloat16).to(torch.float32).contiguous()
+        sin = freqs.sin().to(torch.bfloat16).to(torch.float32).contiguous()
+        self.load_weight("rope.cos", cos)
+        self.load_weight("rope.sin", sin)
+
+    def load_weight(self, key: str, tensor: torch.Tensor):
+        t = tensor.detach()
+        if t.dtype not in _DTYPES:
+            t = t.to(torch.float32)
+        t = t.contiguous()
+        shape = (C.c_int64 * max(1, t.dim()))(*([int(s) for s in t.shape] or [1]))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mjv_load_weight(self._handle, key.encode(), t.data_ptr(), shape, max(1, t.dim()),
+                                                _DTYPES[t.dtype]))
+        self._finalized = False
+
+    def load_state_dict(self, state_dict: dict):
+        for k, v in state_dict.items():
+            self.load_weight(k, v)
+        self.finalize()
+
+    def finalize(self):
+        _lib.check(self.lib.mjv_finalize_weights(self._handle))
+        self._finalized = True
+
+    # -------------------------------------------------------------------------------------------- batch metadata
+    def prepare_batch(self, input_ids: torch.Tensor, attention_mask: torch.Tensor | None, n_tiles: int,
+                      pad_token_id, img_context_token_id: int):
+        """Host-side indexing of a right-padded batch. Returns (meta dict of numpy int32 arrays, scalars)."""
+        ids = input_ids.detach().to("cpu", torch.long).numpy()
+        B, N = ids.shape
+        if pad_token_id is None and B != 1:
+            raise ValueError("Cannot handle batch sizes > 1 if no padding token is defined.")
+        if attention_mask is not None:
+            mask = attention_mask.detach().to("cpu").numpy() != 0
+            lengths = mask.sum(1).astype(np.int64)
+            if not all(mask[b, : lengths[b]].all() for b in range(B)):
+                raise ValueError("attention_mask must be right-padded (contiguous ones then zeros)")
+        else:
+            lengths = np.full(B, N, dtype=np.int64)
+        if (lengths <= 0).any():
+            raise ValueError("empty sequence in batch")
+        # last-token index (moe_reward.py:226-228)
+        if pad_token_id is None:
+            last = np.full(B, N - 1, dtype=np.int64)
+        else:
+            last = ((ids == pad_token_id).astype(np.int32).argmax(-1) - 1) % N
+        gate = np.array([find_token_for_gating(ids[b]) for b in range(B)], dtype=np.int64)
+        for b in range(B):
+            if last[b] >= lengths[b] or gate[b] >= lengths[b]:
+                raise ValueError("the reward/gating token lies in the padded region of the row")
+        cu = np.zeros(B + 1, dtype=np.int64)
+        cu[1:] = np.cumsum(lengths)
+        M = int(cu[-1])
+        token_ids = np.concatenate([ids[b, : lengths[b]] for b in range(B)]).astype(np.int32)
+        row_pos = np.concatenate([np.arange(lengths[b]) for b in range(B)]).astype(np.int32)
+        vt_starts = np.zeros(B, dtype=np.int64)
+        off = 0
+        for b in range(B):
+            vt_starts[b] = off
+            off += (int(lengths[b]) + 7) // 8 * 8
+        vt_cols = off
+        row_vt = np.concatenate([vt_starts[b] + np.arange(lengths[b]) for b in range(B)]).astype(np.int32)
+        img_rows = np.flatnonzero(token_ids == img_context_token_id).astype(np.int32)
+        n_rows_vit = n_tiles * self.dims.tokens_per_tile
+        if img_rows.size > n_rows_vit:
+            # the reference's fallback path raises here too (shape mismatch inside the except branch,
+            # modeling_internvl_chat.py:180-186)
+            raise RuntimeError(f"{img_rows.size} <IMG_CONTEXT> tokens but only {n_rows_vit} visual embeddings")
+        if img_rows.size < n_rows_vit:
+            warnings.warn(f"warning: {n_rows_vit} visual embeddings for {img_rows.size} <IMG_CONTEXT> tokens; "
+                          "truncating like the reference (modeling_internvl_chat.py:178-186)")
+        work = [(s, q) for s in range(B) for q in range((int(lengths[s]) + 127) // 128)]
+        work.sort(key=lambda t: -t[1])
+        work = np.asarray(work, dtype=np.int32).reshape(-1, 2)
+        gather = np.concatenate([cu[:-1] + last, cu[:-1] + gate]).astype(np.int32)
+        meta = dict(token_ids=token_ids, row_pos=row_pos, row_vt=row_vt, img_rows=img_rows,
+                    cu_seqlens=cu.astype(np.int32), vt_starts=vt_starts.astype(np.int32), work=work.reshape(-1),
+                    gather_rows=gather)
+        return meta, dict(B=B, M=M, vt_cols=int(vt_cols), n_work=int(work.shape[0]), n_img=int(img_rows.size),
+                          lengths=lengths, last=last, gate=gate)
+
+    def upload_meta(self, meta: dict) -> tuple[torch.Tensor, dict]:
+        """One pinned staging buffer, one H2D copy; returns the device buffer and the element offset of each section."""
+        offsets, total = {}, 0
+        for k, v in meta.items():
+            offsets[k] = total
+            total += (v.size + 3) // 4 * 4  # keep every section 16-byte aligned
+        host = torch.empty(max(total, 4), dtype=torch.int32, pin_memory=True)
+        hv = host.numpy()
+        for k, v in meta.items():
+            hv[offsets[k]: offsets[k] + v.size] = v
+        dev = host.to(self.device, non_blocking=True)
+        return dev, offsets
+
+    # -------------------------------------------------------------------------------------------- forward
+    def workspace(self, B: int, T: int, M: int) -> torch.Tensor:
+        need = int(self.lib.mjv_workspace_bytes(self._handle, B, T, M))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = None
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def forward(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor | None,
+                pad_token_id, img_context_token_id: int) -> dict:
+        if not self._finalized:
+            self.finalize()
+        d = self.dims
+        if pixel_values.dim() != 4:
+            raise ValueError(f"wrong pixel_values size: {tuple(pixel_values.shape)}")  # modeling_intern_vit.py:410-413
+        T = int(pixel_values.shape[0])
+        meta, info = self.prepare_batch(input_ids, attention_mask, T, pad_token_id, img_context_token_id)
+        with torch.cuda.device(self.device):
+            px = pixel_values.to(self.device)
+            if px.dtype not in (torch.bfloat16, torch.float32):
+                px = px.to(torch.float32)
+            px = px.contiguous()
+            dev_meta, off = self.upload_meta(meta)
+            B, M = info["B"], info["M"]
+            ws = self.workspace(B, T, M)
+            NO, NA, D = d.num_objectives, d.num_aspects, d.llm_hidden
+            scores = torch.empty((B, NO + NA + 1), dtype=torch.float32, device=self.device)
+            extras = torch.empty((B, NO + NA + NO + 1), dtype=torch.float32, device=self.device)
+            hidden = torch.empty((B, D), dtype=torch.bfloat16, device=self.device)
+            prompt = torch.empty((B, D), dtype=torch.bfloat16, device=self.device)
+            base = dev_meta.data_ptr()
+            b = _lib.Batch()
+            b.n_rows, b.n_tiles, b.n_img_tokens, b.n_work = B, T, info["n_img"], info["n_work"]
+            b.img_context_token_id = int(img_context_token_id)
+            b.n_tokens, b.vt_cols = M, info["vt_cols"]
+            b.pixel_values, b.pixel_dtype = px.data_ptr(), _DTYPES[px.dtype]
+            for k in ("token_ids", "row_pos", "row_vt", "img_rows", "cu_seqlens", "vt_starts", "work", "gather_rows"):
+                setattr(b, k, base + 4 * off[k])
+            o = _lib.Outputs()
+            o.scores, o.extras = scores.data_ptr(), extras.data_ptr()
+            o.hidden_state, o.prompt_embedding = hidden.data_ptr(), prompt.data_ptr()
+            _lib.check(self.lib.mjv_score_forward(self._handle, C.byref(b), C.byref(o), ws.data_ptr(), ws.numel(),
+                                                  _lib.current_stream()))
+            # keep the staging buffers alive until the stream has consumed them
+            dev_meta.record_stream(torch.cuda.current_stream())
+            px.record_stream(torch.cuda.current_stream())
+        return dict(scores=scores, extras=extras, hidden_state=hidden, prompt_embedding=prompt, info=info)

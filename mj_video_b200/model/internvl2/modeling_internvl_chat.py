@@ -1,0 +1,187 @@
+"""`prepare_chat_input` and the parameter containers of the VLM backbone.
+
+Reference: scripts/model/internvl2/modeling_internvl_chat.py:36-89 (prepare_chat_input), :100-144 (module tree).
+The containers reproduce the reference's state-dict key space so `load_state_dict(strict=True)`,
+`.to(dtype)`, `.cuda()` and `state_dict()` behave like the reference module; they hold parameters only — all compute is
+in the CUDA library behind `InternVLChatRewardModeling.forward`.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .conversation import get_conv_template
+
+
+def prepare_chat_input(config, tokenizer, pixel_values, question, generation_config, history=None,
+                       return_history=False, num_patches_list=None, IMG_START_TOKEN='<img>', IMG_END_TOKEN='</img>',
+                       IMG_CONTEXT_TOKEN='<IMG_CONTEXT>', verbose=False, device='cpu'):
+    """Build the chat prompt, expand each `<image>` into `<img>` + `<IMG_CONTEXT>`*(tokens*patches) + `</img>` and
+    tokenise it. Same signature, return value and side effect (`generation_config['eos_token_id']`) as the reference."""
+    if history is None and pixel_values is not None and '<image>' not in question:
+        question = '<image>\n' + question
+    if num_patches_list is None:
+        num_patches_list = [pixel_values.shape[0]] if pixel_values is not None else []
+    assert pixel_values is None or len(pixel_values) == sum(num_patches_list)
+
+    template = get_conv_template(config.template)
+    eos_token_id = tokenizer.convert_tokens_to_ids(template.sep.strip())
+    for (old_question, old_answer) in ([] if history is None else history):
+        template.append_message(template.roles[0], old_question)
+        template.append_message(template.roles[1], old_answer)
+    template.append_message(template.roles[0], question)
+    template.append_message(template.roles[1], None)
+    query = template.get_prompt()
+
+    image_size = config.force_image_size or config.vision_config.image_size
+    patch_size = config.vision_config.patch_size
+    num_image_token = int((image_size // patch_size) ** 2 * (config.downsample_ratio ** 2))
+    for num_patches in num_patches_list:
+        image_tokens = IMG_START_TOKEN + IMG_CONTEXT_TOKEN * num_image_token * num_patches + IMG_END_TOKEN
+        query = query.replace('<image>', image_tokens, 1)
+
+    model_inputs = tokenizer(query, return_tensors='pt')
+    input_ids = model_inputs['input_ids'].to(device)
+    attention_mask = model_inputs['attention_mask'].to(device)
+    generation_config['eos_token_id'] = eos_token_id
+    return input_ids, attention_mask
+
+
+# ------------------------------------------------------------------------------------------------ parameter containers
+class _Linear(nn.Module):
+    def __init__(self, in_f, out_f, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_f, in_f), requires_grad=False)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_f), requires_grad=False)
+
+
+class _Norm(nn.Module):
+    def __init__(self, n, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(n), requires_grad=False)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(n), requires_grad=False)
+
+
+class _Empty(nn.Module):
+    pass
+
+
+class _PatchEmbedding(nn.Module):
+    def __init__(self, c_out, ps):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(c_out, 3, ps, ps), requires_grad=False)
+        self.bias = nn.Parameter(torch.empty(c_out), requires_grad=False)
+
+
+def _vision_model(vc) -> nn.Module:
+    C = vc.hidden_size
+    vm = _Empty()
+    emb = _Empty()
+    n_pos = (vc.image_size // vc.patch_size) ** 2 + 1
+    emb.class_embedding = nn.Parameter(torch.empty(1, 1, C), requires_grad=False)
+    emb.position_embedding = nn.Parameter(torch.empty(1, n_pos, C), requires_grad=False)
+    emb.patch_embedding = _PatchEmbedding(C, vc.patch_size)
+    vm.embeddings = emb
+    enc = _Empty()
+    layers = []
+    for _ in range(vc.num_hidden_layers):
+        layer = _Empty()
+        layer.ls1 = nn.Parameter(torch.empty(C), requires_grad=False)
+        layer.ls2 = nn.Parameter(torch.empty(C), requires_grad=False)
+        layer.attn = _Empty()
+        layer.attn.qkv = _Linear(C, 3 * C, bias=vc.qkv_bias)
+        layer.attn.proj = _Linear(C, C)
+        layer.mlp = _Empty()
+        layer.mlp.fc1 = _Linear(C, vc.intermediate_size)
+        layer.mlp.fc2 = _Linear(vc.intermediate_size, C)
+        layer.norm1 = _Norm(C)
+        layer.norm2 = _Norm(C)
+        layers.append(layer)
+    enc.layers = nn.ModuleList(layers)
+    vm.encoder = enc
+    return vm
+
+
+def _language_model(lc) -> nn.Module:
+    D = lc.hidden_size
+    hd = D // lc.num_attention_heads
+    lm = _Empty()
+    core = _Empty()
+    layers = []
+    llama = lc.architectures[0] == "LlamaForCausalLM"
+    if llama:
+        core.embed_tokens = _Linear(D, lc.vocab_size, bias=False)
+    else:
+        core.tok_embeddings = _Linear(D, lc.vocab_size, bias=False)
+    for _ in range(lc.num_hidden_layers):
+        layer = _Empty()
+        if llama:
+            layer.self_attn = _Empty()
+            layer.self_attn.q_proj = _Linear(D, lc.num_attention_heads * hd, bias=False)
+            layer.self_attn.k_proj = _Linear(D, lc.num_key_value_heads * hd, bias=False)
+            layer.self_attn.v_proj = _Linear(D, lc.num_key_value_heads * hd, bias=False)
+            layer.self_attn.o_proj = _Linear(lc.num_attention_heads * hd, D, bias=False)
+            layer.mlp = _Empty()
+            layer.mlp.gate_proj = _Linear(D, lc.intermediate_size, bias=False)
+            layer.mlp.up_proj = _Linear(D, lc.intermediate_size, bias=False)
+            layer.mlp.down_proj = _Linear(lc.intermediate_size, D, bias=False)
+            layer.input_layernorm = _Norm(D, bias=False)
+            layer.post_attention_layernorm = _Norm(D, bias=False)
+        else:
+            layer.attention = _Empty()
+            layer.attention.wqkv = _Linear(D, (lc.num_attention_heads + 2 * lc.num_key_value_heads) * hd, bias=False)
+            layer.attention.wo = _Linear(lc.num_attention_heads * hd, D, bias=False)
+            layer.feed_forward = _Empty()
+            layer.feed_forward.w1 = _Linear(D, lc.intermediate_size, bias=False)
+            layer.feed_forward.w3 = _Linear(D, lc.intermediate_size, bias=False)
+            layer.feed_forward.w2 = _Linear(lc.intermediate_size, D, bias=False)
+            layer.attention_norm = _Norm(D, bias=False)
+            layer.ffn_norm = _Norm(D, bias=False)
+        layers.append(layer)
+    core.layers = nn.ModuleList(layers)
+    core.norm = _Norm(D, bias=False)
+    lm.model = core
+    # the LM head is part of the reference state dict (strict loading) but never used by the reward path
+    if llama:
+        lm.lm_head = _Linear(D, lc.vocab_size, bias=False)
+    else:
+        lm.output = _Linear(D, lc.vocab_size, bias=False)
+    return lm
+
+
+class InternVLChatModel(nn.Module):
+    """Parameter container with the reference's attribute surface: `.vision_model`, `.language_model`, `.mlp1`,
+    `.img_context_token_id`, `.device`, `.template`, `.num_image_token`, `.downsample_ratio`, `.ps_version`."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        image_size = config.force_image_size or config.vision_config.image_size
+        patch_size = config.vision_config.patch_size
+        self.patch_size = patch_size
+        self.select_layer = config.select_layer
+        self.template = config.template
+        self.num_image_token = int((image_size // patch_size) ** 2 * (config.downsample_ratio ** 2))
+        self.downsample_ratio = config.downsample_ratio
+        self.ps_version = config.ps_version
+        vc = config.vision_config
+        if config.force_image_size:
+            vc.image_size = config.force_image_size
+        self.vision_model = _vision_model(vc)
+        self.language_model = _language_model(config.llm_config)
+        C4 = vc.hidden_size * int(1 / self.downsample_ratio) ** 2
+        D = config.llm_config.hidden_size
+        self.mlp1 = nn.Sequential(_Norm(C4), _Linear(C4, D), nn.GELU(), _Linear(D, D))
+        self.img_context_token_id = None
+        self.conv_template = get_conv_template(self.template) if self.template else None
+        self.system_message = self.conv_template.system_message if self.conv_template else None
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype

@@ -1,0 +1,197 @@
+"""Drop-in for scripts/model/moe_reward.py: `InternVLChatRewardModeling`, its config and output container.
+
+Same constructor, attributes, state-dict keys, `forward` signature, output fields/dtypes and exceptions as the reference
+(moe_reward.py:60-89, 92-133, 138-297); the forward itself runs in hand-written sm_100a kernels behind the C ABI
+(include/mjv_b200.h -> mjv_score_forward). There is no PyTorch fallback: without the CUDA library or a CUDA device,
+`forward` raises.
+
+Compute dtype: bf16 with fp32 accumulation, mirroring the rounding points of the reference's `.to(bfloat16)` path
+(SURVEY §A.3). Outputs follow the reference dtypes: `aspect_scores`/`score` fp32, everything else the module dtype.
+"""
+from __future__ import annotations
+
+import glob
+import os
+from collections import OrderedDict
+from dataclasses import dataclass, fields
+from typing import Optional
+
+import torch
+from torch import nn
+
+from ..engine import Engine, EngineDims, find_token_for_gating  # noqa: F401  (re-exported like the reference)
+from .internvl2 import InternVLChatModel, InternVLChatRewardModelingConfig  # noqa: F401
+
+token_pattern = [92542, 92543, 525, 11353, 364]  # moe_reward.py:48
+
+
+class GatingNetwork(nn.Module):
+    """Parameter container of the reference's gating MLP (moe_reward.py:16-42): `layers.{i}.weight/bias`,
+    `logit_scale`, `temperature`. Its math runs inside the fused head kernels of `InternVLChatRewardModeling.forward`."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, temperature: float = 10,
+                 logit_scale: float = 1., hidden_dim: int = 1024, n_hidden: int = 3):
+        super().__init__()
+        self.temperature = temperature
+        self.logit_scale = nn.Parameter(torch.ones(1) * logit_scale)
+        layers = []
+        for _ in range(n_hidden):
+            layers.append(nn.Linear(in_features, hidden_dim))
+            in_features = hidden_dim
+        layers.append(nn.Linear(in_features, out_features, bias=bias))
+        self.layers = nn.ModuleList(layers)
+
+    def forward(self, x):  # pragma: no cover - not a standalone op in this implementation
+        raise NotImplementedError("GatingNetwork is evaluated inside InternVLChatRewardModeling.forward (CUDA head "
+                                  "kernel); there is no standalone / CPU path")
+
+    forward_wo_softmax = forward
+
+
+class CustomOutput(OrderedDict):
+    """Same fields, attribute access, key access and None-dropping as the reference's `ModelOutput` dataclass
+    (moe_reward.py:60-89)."""
+    _FIELDS = ("rewards", "hidden_state", "prompt_embedding", "criteria_gating_output", "aspect_gating_output",
+               "aspect_weights", "score", "weighted_scores", "aspect_scores")
+
+    def __init__(self, **kw):
+        super().__init__()
+        for k in kw:
+            if k not in self._FIELDS:
+                raise TypeError(f"unexpected field {k}")
+        for k in self._FIELDS:
+            v = kw.get(k)
+            object.__setattr__(self, k, v)
+            if v is not None:
+                OrderedDict.__setitem__(self, k, v)
+
+    def __getitem__(self, k):
+        if isinstance(k, str):
+            return OrderedDict.__getitem__(self, k)
+        return self.to_tuple()[k]
+
+    def to_tuple(self):
+        return tuple(self[k] for k in self.keys())
+
+
+def _engine_dims(config) -> EngineDims:
+    vc, lc = config.vision_config, config.llm_config
+    arch = lc.architectures[0]
+    if arch not in ("InternLM2ForCausalLM", "LlamaForCausalLM"):
+        raise NotImplementedError(f"{arch} is not implemented.")  # modeling_internvl_chat.py:125-130
+    if vc.qk_normalization or vc.norm_type != "layer_norm" or not vc.qkv_bias:
+        raise NotImplementedError("only the InternViT-300M flavour (layer_norm, qkv_bias, no qk_normalization) is built")
+    if config.ps_version != "v2" or config.select_layer != -1:
+        raise NotImplementedError("only ps_version='v2' and select_layer=-1 are built")
+    rs = lc.rope_scaling
+    if rs is not None and rs.get("type") not in ("dynamic",):
+        raise NotImplementedError(f"rope_scaling {rs} is not built")
+    return EngineDims(
+        image_size=config.force_image_size or vc.image_size, patch_size=vc.patch_size, vit_hidden=vc.hidden_size,
+        vit_heads=vc.num_attention_heads, vit_mlp=vc.intermediate_size, vit_layers=vc.num_hidden_layers,
+        vit_eps=vc.layer_norm_eps, llm_arch=0 if arch == "InternLM2ForCausalLM" else 1, llm_hidden=lc.hidden_size,
+        llm_inter=lc.intermediate_size, llm_layers=lc.num_hidden_layers, llm_heads=lc.num_attention_heads,
+        llm_kv_heads=lc.num_key_value_heads, vocab=lc.vocab_size, rms_eps=lc.rms_norm_eps, rope_theta=lc.rope_theta,
+        max_pos=lc.max_position_embeddings, num_objectives=config.num_objectives, num_aspects=config.num_aspects,
+        gating_hidden=config.gating_hidden_dim, gating_n_hidden=config.gating_n_hidden,
+        gating_temperature=config.gating_temperature,
+        aspect2criteria={k: list(v) for k, v in config.aspect2criteria.items()},
+        downsample_ratio=config.downsample_ratio)
+
+
+class InternVLChatRewardModeling(nn.Module):
+    def __init__(self, name: str, config):
+        super().__init__()
+        self.num_labels = getattr(config, "num_labels", 2)
+        self.model = InternVLChatModel(config)
+        config_dict = config.to_dict()
+        self.num_objectives = config_dict['num_objectives']
+        self.num_aspects = config_dict['num_aspects']
+        self.aspect2criteria = config_dict['aspect2criteria']
+        # sanity checks of the reference (moe_reward.py:153-157)
+        assert len(self.aspect2criteria) == self.num_aspects
+        assert sum(len(v) for v in self.aspect2criteria.values()) == self.num_objectives
+        temp = []
+        for k in self.aspect2criteria.values():
+            temp += k
+        assert sum(len(set(v)) for v in self.aspect2criteria.values()) == len(set(temp))
+
+        hidden_size = config.llm_config.hidden_size
+        self.regression_layer = nn.Linear(hidden_size, self.num_objectives, bias=False)
+        eye = torch.zeros(self.num_objectives, self.num_objectives)
+        eye[range(self.num_objectives), range(self.num_objectives)] = 1.
+        self.reward_transform_matrix = nn.Parameter(eye)
+        self.reward_transform_matrix.requires_grad = False
+        self.aspect_gating = GatingNetwork(hidden_size, self.num_aspects, temperature=config_dict["gating_temperature"],
+                                           hidden_dim=config_dict["gating_hidden_dim"],
+                                           n_hidden=config_dict["gating_n_hidden"])
+        self.criteria_gating = GatingNetwork(hidden_size, config.num_objectives,
+                                             temperature=config_dict["gating_temperature"],
+                                             hidden_dim=config_dict["gating_hidden_dim"],
+                                             n_hidden=config_dict["gating_n_hidden"])
+        self.config = config
+        self._engine: Engine | None = None
+        self._engine_key = None
+        if name and os.path.isdir(str(name)):
+            self._load_backbone_checkpoint(str(name))
+
+    # ------------------------------------------------------------------ checkpoints (InternVLChatModel.from_pretrained)
+    def _load_backbone_checkpoint(self, path: str):
+        files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+        if not files:
+            return
+        from safetensors.torch import load_file
+        sd = {}
+        for f in files:
+            sd.update(load_file(f))
+        missing, unexpected = self.model.load_state_dict(sd, strict=False)
+        if unexpected:
+            raise RuntimeError(f"unexpected keys in backbone checkpoint: {unexpected[:5]}")
+
+    # ------------------------------------------------------------------ engine sync
+    def _weights_key(self):
+        ps = list(self.parameters())
+        return (ps[0].device, ps[0].dtype, sum(p._version for p in ps), tuple(p.data_ptr() for p in ps[:4]))
+
+    def _get_engine(self) -> Engine:
+        dev = self.model.device
+        if dev.type != "cuda":
+            raise RuntimeError("InternVLChatRewardModeling (mj_video_b200) needs a CUDA device: call .cuda() first; "
+                               "there is no CPU path")
+        key = self._weights_key()
+        if self._engine is None or self._engine.device != dev:
+            self._engine = Engine(_engine_dims(self.config), dev)
+            self._engine_key = None
+        if self._engine_key != key:
+            self._engine.load_state_dict(self.state_dict())
+            self._engine_key = key
+        return self._engine
+
+    def forward(self, pixel_values: torch.FloatTensor, input_ids: torch.LongTensor = None,
+                attention_mask: Optional[torch.Tensor] = None, position_ids=None, image_flags=None,
+                past_key_values=None, labels=None, use_cache=None, output_attentions=None, output_hidden_states=None,
+                return_dict=None) -> CustomOutput:
+        if input_ids is None:
+            raise ValueError("input_ids is required")
+        if position_ids is not None or past_key_values is not None:
+            raise NotImplementedError("position_ids / past_key_values are not used by the scoring path")
+        batch_size = input_ids.shape[0]
+        pad_id = getattr(self.config, "pad_token_id", None)
+        if pad_id is None and batch_size != 1:
+            raise ValueError("Cannot handle batch sizes > 1 if no padding token is defined.")
+        engine = self._get_engine()
+        res = engine.forward(pixel_values, input_ids, attention_mask, pad_id, self.model.img_context_token_id)
+        NO, NA = self.num_objectives, self.num_aspects
+        dt = self.model.dtype
+        s, e = res["scores"], res["extras"]
+        return CustomOutput(
+            rewards=s[:, :NO].to(dt),
+            hidden_state=res["hidden_state"].to(dt),
+            prompt_embedding=res["prompt_embedding"].to(dt),
+            criteria_gating_output=e[:, :NO].to(dt),
+            aspect_gating_output=e[:, NO:NO + NA].to(dt),
+            aspect_weights=e[:, NO + NA:NO + NA + NO].to(dt),
+            weighted_scores=e[:, NO + NA + NO].to(dt),
+            aspect_scores=s[:, NO:NO + NA].contiguous(),
+            score=s[:, NO + NA].contiguous(),
+        )

@@ -151,9 +151,9 @@ def make_state_dict(d: ModelDims, seed: int = 1234, include_lm_head: bool = True
     _norm(sd, g, "model.mlp1.0", c4)
     _linear(sd, g, "model.mlp1.1", D, c4)
     _linear(sd, g, "model.mlp1.3", D, D)
-    # head: nn.Linear defaults; regression scaled so |rewards| ~ 0.3 (a trained +-1 regressor), last gating layers
+    # head: nn.Linear defaults; regression scaled so |rewards| <~ 0.45 (a trained +-1 regressor; SURVEY §8(d).1: x0.25), last gating layers
     # scaled so logits are O(1) and the softmax/argmax is well separated (SURVEY §7 hard parts, §8(d).1)
-    sd["regression_layer.weight"] = _uniform(g, (no, D), 1.0 / math.sqrt(D)) * 0.5
+    sd["regression_layer.weight"] = _uniform(g, (no, D), 1.0 / math.sqrt(D)) * 0.25
     for name, n_out in (("aspect_gating", d.num_aspects), ("criteria_gating", no)):
         sd[f"{name}.logit_scale"] = torch.ones(1)
         in_f = D

@@ -117,6 +117,7 @@ typedef struct mjv_attn_desc {
     int64_t vt_cols;           /* varlen: number of V^T columns in use (<= vt_ld); 0 = total_rows         */
     int32_t n_work;
     float scale;          /* softmax scale (1/sqrt(head_dim))                                             */
+    double flops_hint;    /* varlen: algorithmic FLOPs of this launch for the profiler (0 = unknown)      */
 } mjv_attn_desc;
 
 int mjv_attention(const mjv_attn_desc* desc, void* stream);
@@ -199,6 +200,7 @@ typedef struct mjv_batch {
     int32_t img_context_token_id; /* rows holding this id are written by the projector, not the embedding table */
     int64_t n_tokens;          /* M = sum of real sequence lengths                                            */
     int64_t vt_cols;           /* columns of the transposed-V buffer (sum of 8-aligned lengths)               */
+    double attn_flops;         /* algorithmic FLOPs of ONE causal attention launch: sum_b 4*H*hd*n_b(n_b+1)/2 (profiler only) */
     const void* pixel_values;  /* device [T,3,S,S]                                                            */
     int32_t pixel_dtype;       /* MJV_DTYPE_BF16 or MJV_DTYPE_F32                                             */
     const int32_t* token_ids;  /* device [M] packed token ids                                                 */
@@ -233,8 +235,17 @@ int mjv_reward_head(mjv_handle* h, const void* gathered_2b, int32_t n_rows, cons
 int mjv_score_forward(mjv_handle* h, const mjv_batch* batch, const mjv_outputs* out, void* workspace,
                       int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Launch accounting and per-launch timing (used by bench.py; see csrc/launch.cuh for the tag list).
+ * mjv_profile_enable(mask): bracket every launch whose tag bit is set with two CUDA events on the launching stream.
+ * mjv_profile_read: elapsed ms + algorithmic work (FLOPs or bytes) per recorded launch; clears the records.
+ * ---------------------------------------------------------------------------------------------------------- */
 long long mjv_launch_count(void);
 void mjv_reset_launch_count(void);
+void mjv_profile_enable(uint32_t tag_mask);
+int mjv_profile_read(int32_t* tags, float* ms, double* work, int32_t capacity);
+const char* mjv_kernel_tag_name(int32_t tag);
+int mjv_kernel_tag_count(void);
 
 #ifdef __cplusplus
 }

@@ -42,7 +42,7 @@ class AttnDesc(C.Structure):
         ("q_col0", C.c_int32), ("k_col0", C.c_int32), ("causal", C.c_int32),
         ("nseq", C.c_int32), ("seq_len", C.c_int32),
         ("cu_seqlens", C.c_void_p), ("work", C.c_void_p), ("vt_starts", C.c_void_p), ("vt_cols", C.c_int64),
-        ("n_work", C.c_int32), ("scale", C.c_float),
+        ("n_work", C.c_int32), ("scale", C.c_float), ("flops_hint", C.c_double),
     ]
 
 
@@ -65,7 +65,7 @@ class Batch(C.Structure):
     _fields_ = [
         ("n_rows", C.c_int32), ("n_tiles", C.c_int32), ("n_img_tokens", C.c_int32), ("n_work", C.c_int32),
         ("img_context_token_id", C.c_int32),
-        ("n_tokens", C.c_int64), ("vt_cols", C.c_int64),
+        ("n_tokens", C.c_int64), ("vt_cols", C.c_int64), ("attn_flops", C.c_double),
         ("pixel_values", C.c_void_p), ("pixel_dtype", C.c_int32),
         ("token_ids", C.c_void_p), ("row_pos", C.c_void_p), ("row_vt", C.c_void_p), ("img_rows", C.c_void_p),
         ("cu_seqlens", C.c_void_p), ("vt_starts", C.c_void_p), ("work", C.c_void_p), ("gather_rows", C.c_void_p),
@@ -95,6 +95,13 @@ def load() -> C.CDLL:
     lib.mjv_last_error.restype = C.c_char_p
     lib.mjv_launch_count.restype = C.c_longlong
     lib.mjv_reset_launch_count.restype = None
+    lib.mjv_profile_enable.argtypes = [C.c_uint32]
+    lib.mjv_profile_enable.restype = None
+    lib.mjv_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.mjv_profile_read.restype = C.c_int
+    lib.mjv_kernel_tag_name.argtypes = [C.c_int32]
+    lib.mjv_kernel_tag_name.restype = C.c_char_p
+    lib.mjv_kernel_tag_count.restype = C.c_int
     lib.mjv_gemm_bf16.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     lib.mjv_gemm_bf16.restype = C.c_int
     lib.mjv_attention.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
@@ -143,3 +150,23 @@ def ptr(t) -> int | None:
 def current_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def profile_collect(capacity: int = 1 << 16):
+    import numpy as np
+    lib = load()
+    tags = np.zeros(capacity, np.int32)
+    ms = np.zeros(capacity, np.float32)
+    work = np.zeros(capacity, np.float64)
+    n = lib.mjv_profile_read(tags.ctypes.data, ms.ctypes.data, work.ctypes.data, capacity)
+    n = min(n, capacity)
+    names = [lib.mjv_kernel_tag_name(int(t)).decode() for t in tags[:n]]
+    return list(zip(names, ms[:n].tolist(), work[:n].tolist()))
+
+
+def tag_mask(*names) -> int:
+    lib = load()
+    all_names = [lib.mjv_kernel_tag_name(i).decode() for i in range(lib.mjv_kernel_tag_count())]
+    if not names:
+        return (1 << len(all_names)) - 1
+    return sum(1 << all_names.index(n) for n in names)

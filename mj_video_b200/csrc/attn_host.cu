@@ -7,7 +7,7 @@ namespace mjv {
 
 template <int HD, int BKV, bool CAUSAL>
 static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& a,
-                         dim3 grid, cudaStream_t stream) {
+                         dim3 grid, cudaStream_t stream, double work) {
     using L = attn_detail::Smem<HD, BKV>;
     auto kfn = attention_kernel<HD, BKV, CAUSAL>;
     static bool configured = false;
@@ -16,9 +16,11 @@ static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
         MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    kfn<<<grid, attn_detail::kThreads, L::kTotal, stream>>>(tq, tk, tv, a);
+    {
+        LaunchScope scope(CAUSAL ? TAG_ATTN_CAUSAL : TAG_ATTN_BIDIR, stream, work);
+        kfn<<<grid, attn_detail::kThreads, L::kTotal, stream>>>(tq, tk, tv, a);
+    }
     MJV_CUDA_OK(cudaGetLastError());
-    count_launch();
     return 0;
 }
 
@@ -76,16 +78,19 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     a.scale_log2 = d.scale * 1.4426950408889634f;
     a.batched = varlen ? 0 : 1;
 
+    // algorithmic FLOPs: 4*heads*hd*S^2 per sequence (bidirectional); causal work is supplied by the caller (flops_hint)
+    double work = d.flops_hint;
+    if (!varlen) work = 4.0 * d.heads * hd * (double)d.seq_len * d.seq_len * d.nseq;
     dim3 grid;
     if (varlen) grid = dim3((unsigned)d.n_work, (unsigned)d.heads, 1);
     else grid = dim3((unsigned)((d.seq_len + 127) / 128), (unsigned)d.heads, (unsigned)d.nseq);
 
     if (hd == 64) {
-        if (d.causal) return launch_attn_t<64, 128, true>(tq, tk, tv, a, grid, stream);
-        return launch_attn_t<64, 128, false>(tq, tk, tv, a, grid, stream);
+        if (d.causal) return launch_attn_t<64, 128, true>(tq, tk, tv, a, grid, stream, work);
+        return launch_attn_t<64, 128, false>(tq, tk, tv, a, grid, stream, work);
     }
-    if (d.causal) return launch_attn_t<128, 64, true>(tq, tk, tv, a, grid, stream);
-    return launch_attn_t<128, 64, false>(tq, tk, tv, a, grid, stream);
+    if (d.causal) return launch_attn_t<128, 64, true>(tq, tk, tv, a, grid, stream, work);
+    return launch_attn_t<128, 64, false>(tq, tk, tv, a, grid, stream, work);
 }
 
 }  // namespace mjv

@@ -561,6 +561,7 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
             a.n_work = b.n_work;
             a.vt_starts = b.vt_starts;
             a.vt_cols = b.vt_cols;
+            a.flops_hint = b.attn_flops;
             a.scale = 1.0f / sqrtf(static_cast<float>(d.hd));
             MJV_PROPAGATE(attention(a, st));
         }

@@ -288,9 +288,11 @@ int preprocess_t(const uint8_t* frames, int F, int H, int W, int image_size, int
     const int S = image_size;
     const int grid = sm_count() * 8;
     if (blocks == 1 && W == S && H == S && S % 16 == 0 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0) {
-        normalize_tiles_kernel<TOut><<<grid, 256, 0, st>>>(frames, out, F, S, lut);
+        {
+            LaunchScope scope(TAG_FRAMES, st, (double)F * S * S * 3.0 * (1.0 + sizeof(TOut)));
+            normalize_tiles_kernel<TOut><<<grid, 256, 0, st>>>(frames, out, F, S, lut);
+        }
         MJV_CUDA_OK(cudaGetLastError());
-        count_launch();
         return 0;
     }
     const int OW = S * gi, OH = S * gj;
@@ -300,22 +302,24 @@ int preprocess_t(const uint8_t* frames, int F, int H, int W, int image_size, int
     DeviceCoeffs ch, cv;
     MJV_PROPAGATE(get_device_coeffs(W, OW, st, &ch));
     MJV_PROPAGATE(get_device_coeffs(H, OH, st, &cv));
-    resample_h_kernel<<<grid, 256, 0, st>>>(frames, scratch, F, H, W, OW, ch.bounds, ch.kk, ch.ksize);
+    {
+        LaunchScope scope(TAG_FRAMES, st, (double)F * (3.0 * H * W + 6.0 * H * OW + 3.0 * OW * OH * sizeof(TOut)), 2);
+        resample_h_kernel<<<grid, 256, 0, st>>>(frames, scratch, F, H, W, OW, ch.bounds, ch.kk, ch.ksize);
+        resample_v_tiles_kernel<TOut><<<grid, 256, 0, st>>>(scratch, out, F, H, OW, OH, S, gi, tpf, 0, cv.bounds, cv.kk,
+                                                            cv.ksize, lut);
+    }
     MJV_CUDA_OK(cudaGetLastError());
-    resample_v_tiles_kernel<TOut><<<grid, 256, 0, st>>>(scratch, out, F, H, OW, OH, S, gi, tpf, 0, cv.bounds, cv.kk,
-                                                        cv.ksize, lut);
-    MJV_CUDA_OK(cudaGetLastError());
-    count_launch(2);
     if (tpf > blocks) {  // thumbnail: whole frame -> S x S (data.py:114-116)
         DeviceCoeffs th, tv;
         MJV_PROPAGATE(get_device_coeffs(W, S, st, &th));
         MJV_PROPAGATE(get_device_coeffs(H, S, st, &tv));
-        resample_h_kernel<<<grid, 256, 0, st>>>(frames, scratch, F, H, W, S, th.bounds, th.kk, th.ksize);
+        {
+            LaunchScope scope(TAG_FRAMES, st, (double)F * (3.0 * H * W + 6.0 * H * S + 3.0 * S * S * sizeof(TOut)), 2);
+            resample_h_kernel<<<grid, 256, 0, st>>>(frames, scratch, F, H, W, S, th.bounds, th.kk, th.ksize);
+            resample_v_tiles_kernel<TOut><<<grid, 256, 0, st>>>(scratch, out, F, H, S, S, S, 1, tpf, blocks, tv.bounds,
+                                                                tv.kk, tv.ksize, lut);
+        }
         MJV_CUDA_OK(cudaGetLastError());
-        resample_v_tiles_kernel<TOut><<<grid, 256, 0, st>>>(scratch, out, F, H, S, S, S, 1, tpf, blocks, tv.bounds, tv.kk,
-                                                            tv.ksize, lut);
-        MJV_CUDA_OK(cudaGetLastError());
-        count_launch(2);
     }
     return 0;
 }

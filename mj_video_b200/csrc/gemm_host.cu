@@ -16,9 +16,11 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
     }
     const int tiles = args.num_m_blocks * args.num_n_blocks;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    kfn<<<grid, gemm_detail::kThreads, L::kTotal, stream>>>(tmA, tmB, args);
+    {
+        LaunchScope scope(TAG_GEMM_STORE + EPI, stream, 2.0 * args.M * args.N * args.K);
+        kfn<<<grid, gemm_detail::kThreads, L::kTotal, stream>>>(tmA, tmB, args);
+    }
     MJV_CUDA_OK(cudaGetLastError());
-    count_launch();
     return 0;
 }
 

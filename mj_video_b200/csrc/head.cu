@@ -215,18 +215,24 @@ int skinny_linear(const HeadJobs& jobs, int B, cudaStream_t st) {
         MJV_CHECK(jobs_host[j].K % 8 == 0 && jobs_host[j].ldx % 8 == 0, MJV_ERR_ARG, "head: K/ldx must be multiples of 8");
         blocks += ((jobs_host[j].N + kOutsPerBlock - 1) / kOutsPerBlock) * row_blocks;
     }
-    skinny_linear_kernel<<<blocks, kWarps * 32, 0, st>>>(jobs, B);
+    double bytes = 0;
+    for (int j = 0; j < n_jobs; ++j) bytes += 2.0 * jobs_host[j].N * jobs_host[j].K + 2.0 * B * (jobs_host[j].K + jobs_host[j].N);
+    {
+        LaunchScope scope(TAG_HEAD_LINEAR, st, bytes);
+        skinny_linear_kernel<<<blocks, kWarps * 32, 0, st>>>(jobs, B);
+    }
     MJV_CUDA_OK(cudaGetLastError());
-    count_launch();
     return 0;
 }
 
 int head_finalize(const HeadFinalizeArgs& a, cudaStream_t st) {
     if (a.B == 0) return 0;
     MJV_CHECK(a.num_objectives <= 32 && a.num_aspects <= 32, MJV_ERR_ARG, "head: at most 32 criteria / aspects");
-    head_finalize_kernel<<<(a.B + 3) / 4, 128, 0, st>>>(a);
+    {
+        LaunchScope scope(TAG_HEAD_FINALIZE, st, 0.0);
+        head_finalize_kernel<<<(a.B + 3) / 4, 128, 0, st>>>(a);
+    }
     MJV_CUDA_OK(cudaGetLastError());
-    count_launch();
     return 0;
 }
 

@@ -193,6 +193,7 @@ int launch_ln(const __nv_bfloat16* x, const __nv_bfloat16* w, const __nv_bfloat1
     const int nchunk = (C + 255) / 256;
     const unsigned grid = static_cast<unsigned>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const int threads = kWarpsPerBlock * 32;
+    LaunchScope scope(GATHER ? TAG_PIXSHUF_LN : TAG_LAYERNORM, st, 4.0 * rows * C);
 #define MJV_LN(NC) layernorm_kernel<NC, GATHER><<<grid, threads, 0, st>>>(x, w, b, out, rows, C, eps, ldx, grid_g, seq)
     if (nchunk <= 1) MJV_LN(1);
     else if (nchunk <= 2) MJV_LN(2);
@@ -201,7 +202,6 @@ int launch_ln(const __nv_bfloat16* x, const __nv_bfloat16* w, const __nv_bfloat1
     else MJV_LN(16);
 #undef MJV_LN
     MJV_CUDA_OK(cudaGetLastError());
-    count_launch();
     return 0;
 }
 
@@ -233,6 +233,7 @@ int rmsnorm(const void* x, const void* w, void* out, long long rows, int C, floa
     const int nchunk = (C + 255) / 256;
     const unsigned grid = static_cast<unsigned>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const int threads = kWarpsPerBlock * 32;
+    LaunchScope scope(TAG_RMSNORM, st, 4.0 * rows * C);
 #define MJV_RMS(NC) \
     rmsnorm_kernel<NC><<<grid, threads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)out, rows, C, eps, row_idx)
     if (nchunk <= 1) MJV_RMS(1);
@@ -242,7 +243,6 @@ int rmsnorm(const void* x, const void* w, void* out, long long rows, int C, floa
     else MJV_RMS(16);
 #undef MJV_RMS
     MJV_CUDA_OK(cudaGetLastError());
-    count_launch();
     return 0;
 }
 
@@ -251,10 +251,12 @@ int embed_tokens(const int* ids, const void* table, void* out, long long rows, i
     if (rows == 0) return 0;
     MJV_CHECK(C % 8 == 0, MJV_ERR_ARG, "embed: C=%d", C);
     const unsigned grid = static_cast<unsigned>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    embed_kernel<<<grid, kWarpsPerBlock * 32, 0, st>>>(ids, (const __nv_bfloat16*)table, (__nv_bfloat16*)out, rows, C,
-                                                        img_ctx_id, vocab);
+    {
+        LaunchScope scope(TAG_EMBED, st, 4.0 * rows * C);
+        embed_kernel<<<grid, kWarpsPerBlock * 32, 0, st>>>(ids, (const __nv_bfloat16*)table, (__nv_bfloat16*)out, rows, C,
+                                                            img_ctx_id, vocab);
+    }
     MJV_CUDA_OK(cudaGetLastError());
-    count_launch();
     return 0;
 }
 
@@ -262,6 +264,8 @@ int im2col_patches(const void* px, int px_dtype, void* out, int T, int img, int 
     if (T == 0) return 0;
     MJV_CHECK(img % ps == 0 && Kpad >= 3 * ps * ps && Kpad % 8 == 0, MJV_ERR_ARG, "im2col: bad geometry");
     const int grid = sm_count() * 8;
+    const int g_ = img / ps;
+    LaunchScope scope(TAG_IM2COL, st, (double)T * (3.0 * img * img * (px_dtype == MJV_DTYPE_F32 ? 4 : 2) + 2.0 * g_ * g_ * Kpad));
     if (px_dtype == MJV_DTYPE_BF16)
         im2col_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)px, (__nv_bfloat16*)out, T, img, ps, Kpad);
     else if (px_dtype == MJV_DTYPE_F32)
@@ -269,16 +273,17 @@ int im2col_patches(const void* px, int px_dtype, void* out, int T, int img, int 
     else
         return set_error(MJV_ERR_ARG, "im2col: unsupported pixel dtype %d", px_dtype);
     MJV_CUDA_OK(cudaGetLastError());
-    count_launch();
     return 0;
 }
 
 int cls_rows(const void* cls, const void* pos, void* hidden, int T, int S, int C, cudaStream_t st) {
     if (T == 0) return 0;
-    cls_rows_kernel<<<(T * C + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)cls, (const __nv_bfloat16*)pos,
-                                                         (__nv_bfloat16*)hidden, T, S, C);
+    {
+        LaunchScope scope(TAG_CLS_ROWS, st, 2.0 * T * C);
+        cls_rows_kernel<<<(T * C + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)cls, (const __nv_bfloat16*)pos,
+                                                             (__nv_bfloat16*)hidden, T, S, C);
+    }
     MJV_CUDA_OK(cudaGetLastError());
-    count_launch();
     return 0;
 }
 

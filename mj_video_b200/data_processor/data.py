@@ -113,7 +113,7 @@ def open_video(video):
 
 
 def preprocess_frames(frames_u8: torch.Tensor, input_size=448, max_num=1, use_thumbnail=True,
-                      dtype=torch.float32) -> tuple[torch.Tensor, int]:
+                      dtype=torch.float32, out: torch.Tensor | None = None) -> tuple[torch.Tensor, int]:
     """uint8 CUDA tensor [F,H,W,3] -> normalised tiles [F*tiles_per_frame,3,S,S] on the same device.
     The GPU body of dynamic_preprocess + build_transform; returns (tiles, tiles_per_frame)."""
     lib = _lib.load()
@@ -127,7 +127,10 @@ def preprocess_frames(frames_u8: torch.Tensor, input_size=448, max_num=1, use_th
         st = _lib.current_stream()
         _lib.check(lib.mjv_preprocess_frames(frames_u8.data_ptr(), F, H, W, input_size, max_num, int(use_thumbnail),
                                              None, out_dt, None, 0, C.byref(tpf), st))
-        out = torch.empty((F * tpf.value, 3, input_size, input_size), dtype=dtype, device=frames_u8.device)
+        if out is None:
+            out = torch.empty((F * tpf.value, 3, input_size, input_size), dtype=dtype, device=frames_u8.device)
+        elif out.numel() != F * tpf.value * 3 * input_size * input_size or out.dtype != dtype or not out.is_contiguous():
+            raise ValueError("preprocess_frames: `out` has the wrong size / dtype")
         gi, gj = find_closest_aspect_ratio(W, H, 1, max_num, input_size)
         scratch = None
         if not (gi * gj == 1 and H == input_size and W == input_size):

@@ -242,8 +242,10 @@ class Engine:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._workspace
 
-    def forward(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor | None,
-                pad_token_id, img_context_token_id: int) -> dict:
+    def stage_batch(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor | None,
+                    pad_token_id, img_context_token_id: int) -> "StagedBatch":
+        """Index the batch on the host, upload the index metadata (one H2D copy) and allocate outputs. The returned
+        object can be launched any number of times with `run` (its inputs then already live in HBM)."""
         if not self._finalized:
             self.finalize()
         d = self.dims
@@ -252,32 +254,56 @@ class Engine:
         T = int(pixel_values.shape[0])
         meta, info = self.prepare_batch(input_ids, attention_mask, T, pad_token_id, img_context_token_id)
         with torch.cuda.device(self.device):
-            px = pixel_values.to(self.device)
+            px = pixel_values.to(self.device, non_blocking=True)
             if px.dtype not in (torch.bfloat16, torch.float32):
                 px = px.to(torch.float32)
             px = px.contiguous()
             dev_meta, off = self.upload_meta(meta)
             B, M = info["B"], info["M"]
-            ws = self.workspace(B, T, M)
             NO, NA, D = d.num_objectives, d.num_aspects, d.llm_hidden
-            scores = torch.empty((B, NO + NA + 1), dtype=torch.float32, device=self.device)
-            extras = torch.empty((B, NO + NA + NO + 1), dtype=torch.float32, device=self.device)
-            hidden = torch.empty((B, D), dtype=torch.bfloat16, device=self.device)
-            prompt = torch.empty((B, D), dtype=torch.bfloat16, device=self.device)
+            sb = StagedBatch()
+            sb.info = info
+            sb.px, sb.dev_meta = px, dev_meta
+            sb.scores = torch.empty((B, NO + NA + 1), dtype=torch.float32, device=self.device)
+            sb.extras = torch.empty((B, NO + NA + NO + 1), dtype=torch.float32, device=self.device)
+            sb.hidden = torch.empty((B, D), dtype=torch.bfloat16, device=self.device)
+            sb.prompt = torch.empty((B, D), dtype=torch.bfloat16, device=self.device)
             base = dev_meta.data_ptr()
             b = _lib.Batch()
             b.n_rows, b.n_tiles, b.n_img_tokens, b.n_work = B, T, info["n_img"], info["n_work"]
             b.img_context_token_id = int(img_context_token_id)
             b.n_tokens, b.vt_cols = M, info["vt_cols"]
+            hd = d.llm_hidden // d.llm_heads
+            b.attn_flops = float(sum(4.0 * d.llm_heads * hd * n * (n + 1) / 2 for n in info["lengths"].tolist()))
             b.pixel_values, b.pixel_dtype = px.data_ptr(), _DTYPES[px.dtype]
             for k in ("token_ids", "row_pos", "row_vt", "img_rows", "cu_seqlens", "vt_starts", "work", "gather_rows"):
                 setattr(b, k, base + 4 * off[k])
             o = _lib.Outputs()
-            o.scores, o.extras = scores.data_ptr(), extras.data_ptr()
-            o.hidden_state, o.prompt_embedding = hidden.data_ptr(), prompt.data_ptr()
-            _lib.check(self.lib.mjv_score_forward(self._handle, C.byref(b), C.byref(o), ws.data_ptr(), ws.numel(),
-                                                  _lib.current_stream()))
-            # keep the staging buffers alive until the stream has consumed them
-            dev_meta.record_stream(torch.cuda.current_stream())
-            px.record_stream(torch.cuda.current_stream())
-        return dict(scores=scores, extras=extras, hidden_state=hidden, prompt_embedding=prompt, info=info)
+            o.scores, o.extras = sb.scores.data_ptr(), sb.extras.data_ptr()
+            o.hidden_state, o.prompt_embedding = sb.hidden.data_ptr(), sb.prompt.data_ptr()
+            sb.batch, sb.outputs = b, o
+            sb.B, sb.T, sb.M = B, T, M
+        return sb
+
+    def run(self, sb: "StagedBatch") -> dict:
+        """Enqueue the whole forward on the current stream (no synchronisation)."""
+        with torch.cuda.device(self.device):
+            ws = self.workspace(sb.B, sb.T, sb.M)
+            _lib.check(self.lib.mjv_score_forward(self._handle, C.byref(sb.batch), C.byref(sb.outputs), ws.data_ptr(),
+                                                  ws.numel(), _lib.current_stream()))
+        return dict(scores=sb.scores, extras=sb.extras, hidden_state=sb.hidden, prompt_embedding=sb.prompt,
+                    info=sb.info)
+
+    def forward(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor | None,
+                pad_token_id, img_context_token_id: int) -> dict:
+        sb = self.stage_batch(pixel_values, input_ids, attention_mask, pad_token_id, img_context_token_id)
+        out = self.run(sb)
+        # keep the staging buffers alive until the stream has consumed them
+        sb.dev_meta.record_stream(torch.cuda.current_stream(self.device))
+        sb.px.record_stream(torch.cuda.current_stream(self.device))
+        return out
+
+
+class StagedBatch:
+    """Device-resident inputs + index metadata + output buffers of one batch (see Engine.stage_batch)."""
+    pass

@@ -1,0 +1,46 @@
+"""Frame kernels on the B200: bit-exact against the reference's load_video (golden checksums) and the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _sha(t):
+    return hashlib.sha256(t.contiguous().cpu().numpy().tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", ["448x448_m1", "896x1344_m6", "1024x1024_m6", "720x1280_m6", "1280x720_m6",
+                                  "320x512_m6", "100x77_m1", "500x300_m4"])
+def test_load_video_bit_exact_vs_reference_golden(built_lib, golden_frames, name):
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    g = golden_frames[name]
+    v = synth.make_video(g["video_id"], n_frames=g["n_frames"], height=g["H"], width=g["W"])
+    pv, counts = load_video(v, num_segments=g["num_segments"], max_num=g["max_num"])
+    assert pv.device.type == "cpu" and pv.dtype == torch.float32        # reference return contract
+    assert counts == g["counts"] and list(pv.shape) == g["shape"]
+    assert _sha(pv) == g["sha256"]
+    pv16, _ = load_video(v, num_segments=g["num_segments"], max_num=g["max_num"], device="cuda", dtype=torch.bfloat16)
+    assert torch.equal(pv16.cpu(), pv.to(torch.bfloat16))               # == pixel_values.to(bfloat16) of the caller
+
+
+def test_large_batch_identity_path_roundtrip(built_lib):
+    """Full-size property check (256 tiles): the LUT normalisation is invertible, so frames are recovered exactly."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from mj_video_b200.data_processor import preprocess_frames
+    g = torch.Generator(device="cuda").manual_seed(0)
+    frames = torch.randint(0, 256, (256, 448, 448, 3), dtype=torch.uint8, device="cuda", generator=g)
+    out, tpf = preprocess_frames(frames, 448, 1, True, torch.float32)
+    assert tpf == 1 and out.shape == (256, 3, 448, 448)
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda").view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda").view(1, 3, 1, 1)
+    back = torch.round((out * std + mean) * 255).to(torch.uint8).permute(0, 2, 3, 1)
+    assert torch.equal(back, frames)
+    ref = (frames[:4].permute(0, 3, 1, 2).float().div(255) - mean) / std
+    assert torch.equal(out[:4], ref)

@@ -1,0 +1,188 @@
+"""Host-side logic of the product (no GPU): index semantics, prompt building, configs, ABI surface, sharding."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, reference_available
+from mj_video_b200 import synth
+from mj_video_b200.engine import find_token_for_gating
+from oracle import port
+
+
+def test_find_token_for_gating_semantics():
+    pat = synth.GATING_PATTERN
+    seq = [5, 6] + pat + [9, 9] + pat + [1]
+    assert find_token_for_gating(seq) == port.find_token_for_gating(seq) == 9  # LAST occurrence
+    assert find_token_for_gating(pat) == 0
+    with pytest.raises(ValueError, match="Token pattern not found"):
+        find_token_for_gating([1, 2, 3])
+    with pytest.raises(ValueError):
+        find_token_for_gating(pat[:-1])
+
+
+def _engine_stub():
+    """Engine.prepare_batch is pure host code; build an instance without touching CUDA."""
+    from mj_video_b200.engine import Engine, EngineDims
+    e = Engine.__new__(Engine)
+    e.dims = EngineDims.from_synth(synth.dims_tiny())
+    return e
+
+
+def test_prepare_batch_indices_match_reference_semantics():
+    e = _engine_stub()
+    rows = [synth.make_input_ids(i, [1] * 8, n_cap=n) for i, n in enumerate([46, 17, 90])]
+    ids, mask = synth.pad_batch(rows)
+    meta, info = e.prepare_batch(ids, mask, 24, synth.PAD, synth.IMG_CONTEXT)
+    last = port.sequence_end_index(ids, synth.PAD)
+    assert info["last"].tolist() == last.tolist() == [len(r) - 1 for r in rows]
+    assert info["gate"].tolist() == [port.find_token_for_gating(r) for r in rows]
+    cu = meta["cu_seqlens"]
+    assert cu.tolist() == [0] + list(np.cumsum([len(r) for r in rows]))
+    assert meta["token_ids"].tolist() == sum(rows, [])
+    assert (meta["vt_starts"] % 8 == 0).all()                      # TMA needs 16-byte aligned V^T starts
+    assert meta["img_rows"].size == 24 * 256
+    assert (meta["token_ids"][meta["img_rows"]] == synth.IMG_CONTEXT).all()
+    assert meta["gather_rows"].tolist() == [cu[b] + len(rows[b]) - 1 for b in range(3)] + \
+        [cu[b] + port.find_token_for_gating(rows[b]) for b in range(3)]
+    # work list: every (sequence, 128-row block) once, heaviest first
+    work = meta["work"].reshape(-1, 2)
+    assert sorted(map(tuple, work.tolist())) == sorted((s, q) for s in range(3) for q in range((len(rows[s]) + 127) // 128))
+    assert (np.diff(work[:, 1]) <= 0).all()
+
+
+def test_prepare_batch_errors():
+    e = _engine_stub()
+    rows = [synth.make_input_ids(0, [1] * 8, n_cap=20), synth.make_input_ids(1, [1] * 8, n_cap=30)]
+    ids, mask = synth.pad_batch(rows)
+    with pytest.raises(ValueError, match="Cannot handle batch sizes > 1"):       # moe_reward.py:218-219
+        e.prepare_batch(ids, mask, 16, None, synth.IMG_CONTEXT)
+    bad = ids.clone()
+    bad[0, len(rows[0]) - 5:len(rows[0])] = 11
+    with pytest.raises(ValueError, match="Token pattern not found"):             # moe_reward.py:57
+        e.prepare_batch(bad, mask, 16, synth.PAD, synth.IMG_CONTEXT)
+    with pytest.raises(RuntimeError, match="visual embeddings"):                  # more image tokens than ViT rows
+        e.prepare_batch(ids, mask, 15, synth.PAD, synth.IMG_CONTEXT)
+    with pytest.warns(UserWarning, match="truncating"):                           # modeling_internvl_chat.py:178-186
+        meta, info = e.prepare_batch(ids, mask, 17, synth.PAD, synth.IMG_CONTEXT)
+    assert info["n_img"] == 16 * 256
+
+
+def test_single_row_without_pad_token():
+    e = _engine_stub()
+    rows = [synth.make_input_ids(0, [1] * 8, n_cap=20)]
+    ids, mask = synth.pad_batch(rows)
+    meta, info = e.prepare_batch(ids, None, 8, None, synth.IMG_CONTEXT)
+    assert info["last"].tolist() == [ids.shape[1] - 1]
+
+
+def test_prepare_chat_input_matches_reference_golden(golden_chat):
+    import hashlib
+    from mj_video_b200.model import InternVLChatRewardModelingConfig, prepare_chat_input
+    from oracle.make_golden import StubTokenizer
+    d = synth.dims_tiny()
+    cfg = InternVLChatRewardModelingConfig(
+        vision_config=dict(image_size=448, patch_size=14, hidden_size=d.vit_hidden), llm_config=dict(hidden_size=256),
+        template="internlm2-chat", downsample_ratio=0.5, force_image_size=448)
+    for name, g in golden_chat.items():
+        gen = {}
+        ids, mask = prepare_chat_input(cfg, StubTokenizer(), torch.zeros(g["n_tiles"], 3, 448, 448), g["question"], gen,
+                                       num_patches_list=g["num_patches_list"])
+        assert gen["eos_token_id"] == g["eos"]
+        assert ids.shape[1] == g["n"] and int((ids == 92546).sum()) == g["n_img"], name
+        assert ids[0, :60].tolist() == g["head"] and ids[0, -12:].tolist() == g["tail"]
+        assert hashlib.sha256(ids.contiguous().numpy().tobytes()).hexdigest() == g["sha256"]
+        assert torch.equal(mask, torch.ones_like(ids))
+    with pytest.raises(AssertionError):   # tile-count mismatch (modeling_internvl_chat.py:49)
+        prepare_chat_input(cfg, StubTokenizer(), torch.zeros(3, 3, 448, 448), "<image>", {}, num_patches_list=[1, 1])
+
+
+def test_config_and_module_surface():
+    from mj_video_b200.model import InternVLChatRewardModeling, InternVLChatRewardModelingConfig
+    with pytest.raises(ValueError, match="Unsupported architecture"):      # configuration_internvl_chat.py:50-55
+        InternVLChatRewardModelingConfig(llm_config={"architectures": ["Phi3ForCausalLM"]})
+    d = synth.dims_tiny()
+    vision = dict(hidden_size=d.vit_hidden, num_attention_heads=d.vit_heads, intermediate_size=d.vit_mlp,
+                  num_hidden_layers=d.vit_layers, image_size=448, patch_size=14, qkv_bias=True, qk_normalization=False,
+                  norm_type="layer_norm", layer_norm_eps=1e-6)
+    llm = dict(architectures=["InternLM2ForCausalLM"], hidden_size=d.llm_hidden, intermediate_size=d.llm_inter,
+               num_hidden_layers=d.llm_layers, num_attention_heads=d.llm_heads, num_key_value_heads=d.llm_kv_heads,
+               vocab_size=d.vocab, rms_norm_eps=1e-5, bias=False, rope_theta=1e6, max_position_embeddings=32768)
+    cfg = InternVLChatRewardModelingConfig(vision_config=vision, llm_config=llm, template="internlm2-chat",
+                                           ps_version="v2", force_image_size=448, num_objectives=28, num_aspects=5,
+                                           aspect2criteria=d.aspect2criteria, gating_hidden_dim=d.gating_hidden)
+    assert all(k in cfg.to_dict() for k in ("num_objectives", "num_aspects", "aspect2criteria", "gating_temperature",
+                                            "gating_hidden_dim", "gating_n_hidden"))
+    m = InternVLChatRewardModeling("unused", cfg)
+    sd = synth.make_state_dict(d, seed=1)
+    assert set(m.state_dict().keys()) == set(sd.keys())                    # SURVEY §A.2 key space
+    m.load_state_dict(sd, strict=True)
+    m.config.pad_token_id = 2
+    m.model.img_context_token_id = synth.IMG_CONTEXT
+    assert not m.reward_transform_matrix.requires_grad
+    ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=10)])
+    with pytest.raises(RuntimeError, match="CUDA"):                        # no CPU fallback
+        m.forward(torch.zeros(8, 3, 448, 448), ids, mask)
+    with pytest.raises(AssertionError):                                    # moe_reward.py:153-157
+        bad = InternVLChatRewardModelingConfig(vision_config=vision, llm_config=llm, template="internlm2-chat",
+                                               num_objectives=28, num_aspects=4, aspect2criteria=d.aspect2criteria)
+        InternVLChatRewardModeling("unused", bad)
+
+
+def test_abi_exports_every_declared_symbol(built_lib):
+    """include/mjv_b200.h is the drop-in boundary: every function it declares must be exported by the library."""
+    hdr = open(os.path.join(ROOT, "include", "mjv_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(mjv_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 25
+    for n in sorted(names):
+        assert hasattr(built_lib, n), f"{n} declared in include/mjv_b200.h but not exported"
+    assert built_lib.mjv_abi_version() == 1
+
+
+def test_host_helpers_of_the_library(built_lib):
+    """Pure-host entry points: grid choice and the Pillow coefficient tables equal the oracle's."""
+    gi, gj = C.c_int32(), C.c_int32()
+    for (w, h, mx) in [(448, 448, 1), (1344, 896, 6), (1024, 1024, 6), (1280, 720, 6), (720, 1280, 6), (512, 320, 6),
+                       (300, 500, 4), (1920, 1080, 12), (77, 100, 1)]:
+        assert built_lib.mjv_choose_grid(w, h, 1, mx, 448, C.byref(gi), C.byref(gj)) == 0
+        assert (gi.value, gj.value) == port.choose_grid(w, h, 1, mx, 448)
+    for (i, o) in [(1280, 896), (720, 448), (100, 448), (320, 896), (1920, 1344), (333, 448), (2160, 448)]:
+        ks = C.c_int32()
+        assert built_lib.mjv_bicubic_coeffs(i, o, C.byref(ks), None, None, 0) == 0
+        b = np.zeros(2 * o, np.int32)
+        kk = np.zeros(o * ks.value, np.int32)
+        assert built_lib.mjv_bicubic_coeffs(i, o, C.byref(ks), b.ctypes.data, kk.ctypes.data, kk.size) == 0
+        xmin, cnt, pk = port.bicubic_coeffs(i, o)
+        assert (b[0::2] == xmin).all() and (b[1::2] == cnt).all() and (pk == kk.reshape(o, ks.value)).all()
+    assert built_lib.mjv_choose_grid(0, 5, 1, 1, 448, C.byref(gi), C.byref(gj)) < 0
+    assert b"bad args" in built_lib.mjv_last_error()
+
+
+def test_compute_entry_points_fail_loudly_without_gpu(built_lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mj_video_b200 import _lib
+    from mj_video_b200.engine import Engine, EngineDims
+    with pytest.raises(_lib.MjvError):
+        Engine(EngineDims.from_synth(synth.dims_tiny()), "cpu")
+    cfg = _lib.Config()
+    cfg.image_size, cfg.patch_size, cfg.vit_hidden, cfg.llm_hidden = 448, 14, 128, 256
+    cfg.num_objectives, cfg.num_aspects, cfg.gating_n_hidden = 28, 5, 3
+    h = C.c_void_p()
+    assert built_lib.mjv_create(C.byref(cfg), C.byref(h)) == -2        # MJV_ERR_CUDA: no device, no fallback
+    assert b"no CUDA device" in built_lib.mjv_last_error()
+
+
+def test_pair_sharding():
+    from mj_video_b200.dist import pair_rows, preference_decisions, shard_pairs
+    for n, w in [(4096, 8), (4096, 2), (10, 4), (3, 8), (0, 2)]:
+        blocks = [list(shard_pairs(n, r, w)) for r in range(w)]
+        assert sum(blocks, []) == list(range(n))
+        assert max(len(b) for b in blocks) - min(len(b) for b in blocks) <= (n + w - 1) // w
+    assert pair_rows(range(2, 4)) == [(4, 5), (6, 7)]                      # chosen/rejected stay together
+    s = torch.tensor([0.3, 0.1, 0.2, 0.2, -1.0, 0.5])
+    assert preference_decisions(s).tolist() == [0, 1, 1]                    # ~(s0 > s1): ties -> video_1

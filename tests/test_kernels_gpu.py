@@ -1,0 +1,255 @@
+"""Per-kernel parity on the B200: every CUDA kernel family, called through the C ABI, against a plain PyTorch fp32
+reference of the same op that mirrors the reference's bf16 rounding points.
+Tolerances: results are bf16, so one bf16 ulp of the output magnitude (2^-8 relative) is the floor."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from mj_video_b200 import ops as _ops
+    return _ops
+
+
+def close(got, ref, ulps=2.0):
+    got, ref = got.float(), ref.float()
+    tol = ulps * 2.0 ** -8 * max(1.0, ref.abs().max().item())
+    err = (got - ref).abs().max().item()
+    assert not torch.isnan(got).any() and err <= tol, f"max err {err:.4e} > tol {tol:.4e}"
+
+
+def mm(a, w):
+    return a.float() @ w.float().t()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (128, 256, 64, 256), (256, 512, 1024, 256),
+                                      (1000, 384, 576, 128), (4100, 1024, 1024, 256), (333, 256, 640, 256),
+                                      (1, 128, 8, 128), (129, 256, 72, 0)])
+def test_gemm_store_shapes(ops, M, N, K, bn):
+    """Ragged M (TMA zero-fill + row predicate), K not a multiple of 64, both tile widths."""
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.5).bfloat16()
+    out = ops.gemm(a, w, block_n=bn)
+    close(out, mm(a, w).bfloat16())
+
+
+def test_gemm_epilogues(ops):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    M, N, K = 1000, 1024, 512
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.1).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g).bfloat16()
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    ls = torch.randn(N, device="cuda", generator=g).bfloat16()
+    acc = mm(a, w)
+    lin = (acc + bias.float()).bfloat16()
+    close(ops.gemm(a, w, bias=bias), lin)
+    close(ops.gemm(a, w, bias=bias, epilogue=ops.EPI_GELU), torch.nn.functional.gelu(lin.float()).bfloat16())
+    t = (lin.float() * ls.float()).bfloat16()
+    close(ops.gemm(a, w, bias=bias, residual=res, scale=ls, epilogue=ops.EPI_RESID), (res.float() + t.float()).bfloat16())
+    close(ops.gemm(a, w, residual=res, epilogue=ops.EPI_RESID), (res.float() + acc.bfloat16().float()).bfloat16())
+    # in-place residual (out aliases residual), as the engine uses it
+    buf = res.clone()
+    ops.gemm(a, w, out=buf, residual=buf, epilogue=ops.EPI_RESID)
+    close(buf, (res.float() + acc.bfloat16().float()).bfloat16())
+    # SwiGLU with [32 gate | 32 up] interleaved rows
+    F = 512
+    w1 = (torch.randn(F, K, device="cuda", generator=g) * 0.1).bfloat16()
+    w3 = (torch.randn(F, K, device="cuda", generator=g) * 0.1).bfloat16()
+    packed = torch.stack([w1.view(F // 32, 32, K), w3.view(F // 32, 32, K)], dim=1).reshape(2 * F, K).contiguous()
+    gate, up = mm(a, w1).bfloat16(), mm(a, w3).bfloat16()
+    close(ops.gemm(a, packed, epilogue=ops.EPI_SWIGLU), torch.nn.functional.silu(gate.float()).bfloat16() * up)
+    # scatter (the <IMG_CONTEXT> splice)
+    perm = torch.randperm(M, device="cuda", generator=g).int()
+    outbuf = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out=outbuf, bias=bias, row_map=perm, epilogue=ops.EPI_SCATTER)
+    ref = torch.zeros(M, N, device="cuda")
+    ref[perm.long()] = lin.float()
+    close(outbuf, ref)
+    # patch-embed: out row = m + m/P + 1, + bias + pos[m%P + 1]
+    P, T = 256, 3
+    a2 = (torch.randn(T * P, K, device="cuda", generator=g) * 0.5).bfloat16()
+    pos = torch.randn(P + 1, N, device="cuda", generator=g).bfloat16()
+    hid = torch.zeros(T * (P + 1), N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a2, w, out=hid, bias=bias, pos_emb=pos, seq=P, epilogue=ops.EPI_PATCH)
+    ref = ((mm(a2, w) + bias.float()).bfloat16().view(T, P, N) + pos[1:]).float()
+    close(hid.view(T, P + 1, N)[:, 1:], ref.bfloat16())
+    assert hid.view(T, P + 1, N)[:, 0].abs().max() == 0       # CLS rows untouched by the GEMM
+
+
+def test_gemm_qkv_epilogues(ops):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    # ViT: +bias, q|k packed, V transposed per (tile, head)
+    T, S, H = 2, 1025, 2
+    Cv = H * 64
+    x = (torch.randn(T * S, Cv, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(3 * Cv, Cv, device="cuda", generator=g) * 0.1).bfloat16()
+    b = torch.randn(3 * Cv, device="cuda", generator=g).bfloat16()
+    S_pad = (S + 7) // 8 * 8
+    qk = torch.zeros(T * S, 2 * Cv, device="cuda", dtype=torch.bfloat16)
+    vt = torch.zeros(T * H, 64, S_pad, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, w, out=qk, epilogue=ops.EPI_QKV_VIT, bias=b, out_vt=vt, n_q_cols=Cv, n_k_cols=Cv,
+             vt_stride_head=64 * S_pad, vt_ld=S_pad, seq=S, heads=H, block_n=128)
+    ref = (mm(x, w) + b.float()).bfloat16()
+    close(qk, ref[:, :2 * Cv])
+    close(vt[:, :, :S], ref[:, 2 * Cv:].reshape(T, S, H, 64).permute(0, 2, 3, 1).reshape(T * H, 64, S))
+    # LLM: rows [q heads | k heads | v heads] x 128, RoPE with bf16 rounding points, V^T at mapped columns
+    tot, D, Hq, Hkv = 777, 256, 2, 1
+    x = (torch.randn(tot, D, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn((Hq + 2 * Hkv) * 128, D, device="cuda", generator=g) * 0.1).bfloat16()
+    pos = (torch.arange(tot, device="cuda") % 400).int()
+    inv = 1.0 / (1e6 ** (torch.arange(0, 128, 2, device="cuda").float() / 128))
+    fr = torch.outer(torch.arange(512, device="cuda").float(), inv)
+    cos, sin = fr.cos().bfloat16().float().contiguous(), fr.sin().bfloat16().float().contiguous()
+    row_vt = (torch.arange(tot, device="cuda") + 8 * (torch.arange(tot, device="cuda") // 300)).int()
+    vt_cols = int(row_vt.max().item()) // 8 * 8 + 8
+    qo = torch.zeros(tot, Hq * 128, device="cuda", dtype=torch.bfloat16)
+    ko = torch.zeros(tot, Hkv * 128, device="cuda", dtype=torch.bfloat16)
+    vt = torch.zeros(Hkv, 128, vt_cols, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, w, out=qo, epilogue=ops.EPI_QKV_LLM, out_k=ko, out_vt=vt, rope_cos=cos, rope_sin=sin, row_pos=pos,
+             row_vt=row_vt, n_q_cols=Hq * 128, n_k_cols=Hkv * 128, vt_stride_head=128 * vt_cols, vt_ld=vt_cols,
+             block_n=128)
+    y = mm(x, w).bfloat16()
+
+    def rope(t):
+        c = torch.cat([cos, cos], -1)[pos.long()].bfloat16()[:, None, :]
+        s = torch.cat([sin, sin], -1)[pos.long()].bfloat16()[:, None, :]
+        rot = torch.cat([-t[..., 64:], t[..., :64]], -1)
+        return (t * c) + (rot * s)
+
+    close(qo, rope(y[:, :Hq * 128].reshape(tot, Hq, 128)).reshape(tot, -1))
+    close(ko, rope(y[:, Hq * 128:(Hq + Hkv) * 128].reshape(tot, Hkv, 128)).reshape(tot, -1))
+    close(vt[:, :, row_vt.long()], y[:, (Hq + Hkv) * 128:].reshape(tot, Hkv, 128).permute(1, 2, 0))
+
+
+def ref_attn(q, k, v, causal, scale):
+    H, Hkv = q.shape[1], k.shape[1]
+    k = k.repeat_interleave(H // Hkv, dim=1)
+    v = v.repeat_interleave(H // Hkv, dim=1)
+    s = torch.einsum("qhd,khd->hqk", q, k) * scale
+    if causal:
+        S = q.shape[0]
+        s = s.masked_fill(torch.ones(S, S, device=q.device, dtype=torch.bool).triu(1), float("-inf"))
+    return torch.einsum("hqk,khd->qhd", s.softmax(-1), v).reshape(q.shape[0], -1)
+
+
+@pytest.mark.parametrize("T,S,H", [(1, 1, 1), (1, 128, 1), (2, 129, 2), (1, 257, 2), (3, 1025, 2)])
+def test_attention_bidirectional(ops, T, S, H):
+    """ViT shape (hd 64): ragged S incl. the 1-row tail block of S=1025 and the degenerate S=1."""
+    g = torch.Generator(device="cuda").manual_seed(S)
+    Cv = H * 64
+    q, k, v = [torch.randn(T * S, H, 64, device="cuda", generator=g).bfloat16() for _ in range(3)]
+    qk = torch.cat([q.reshape(T * S, Cv), k.reshape(T * S, Cv)], dim=1).contiguous()
+    S_pad = (S + 7) // 8 * 8
+    vt = torch.zeros(T * H, 64, S_pad, device="cuda", dtype=torch.bfloat16)
+    vt[:, :, :S] = v.reshape(T, S, H, 64).permute(0, 2, 3, 1).reshape(T * H, 64, S)
+    out = torch.zeros(T * S, Cv, device="cuda", dtype=torch.bfloat16)
+    ops.attention(qk, qk, vt, out, head_dim=64, heads=H, kv_heads=H, causal=False, scale=0.125, q_col0=0, k_col0=Cv,
+                  nseq=T, seq_len=S)
+    ref = torch.cat([ref_attn(q[t * S:(t + 1) * S].float(), k[t * S:(t + 1) * S].float(), v[t * S:(t + 1) * S].float(),
+                              False, 0.125) for t in range(T)])
+    assert (out.float() - ref).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("lens,H,Hkv", [([1], 1, 1), ([128], 2, 1), ([300, 77, 513], 4, 2), ([2187, 2100], 16, 8),
+                                         ([63, 64, 65, 1, 129], 2, 2)])
+def test_attention_causal_varlen_gqa(ops, lens, H, Hkv):
+    """LLM shape (hd 128): packed ragged sequences, GQA, unaligned sequence starts, single-token rows."""
+    g = torch.Generator(device="cuda").manual_seed(sum(lens))
+    tot = sum(lens)
+    q = torch.randn(tot, H, 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(tot, Hkv, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(tot, Hkv, 128, device="cuda", generator=g).bfloat16()
+    starts, vt_cols = ops.vt_layout(lens)
+    vt = torch.zeros(Hkv, 128, vt_cols, device="cuda", dtype=torch.bfloat16)
+    o = 0
+    for st, n in zip(starts, lens):
+        vt[:, :, st:st + n] = v[o:o + n].permute(1, 2, 0)
+        o += n
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    out = torch.zeros(tot, H * 128, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q.reshape(tot, -1), k.reshape(tot, -1), vt, out, head_dim=128, heads=H, kv_heads=Hkv, causal=True,
+                  scale=1 / math.sqrt(128), cu_seqlens=cu, work=ops.causal_work_list(lens).cuda(),
+                  vt_starts=torch.tensor(starts, dtype=torch.int32, device="cuda"), vt_cols=vt_cols)
+    refs, o = [], 0
+    for n in lens:
+        refs.append(ref_attn(q[o:o + n].float(), k[o:o + n].float(), v[o:o + n].float(), True, 1 / math.sqrt(128)))
+        o += n
+    assert (out.float() - torch.cat(refs)).abs().max().item() < 2e-2
+
+
+def test_attention_large_logits_rescale_path(ops):
+    """Scores that grow along the sequence force the lazy in-TMEM rescale of the output accumulator."""
+    S, H = 1025, 1
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn(S, H, 64, device="cuda", generator=g).bfloat16()
+    k = (torch.randn(S, H, 64, device="cuda", generator=g) * torch.linspace(0.2, 6.0, S, device="cuda")[:, None, None]).bfloat16()
+    v = torch.randn(S, H, 64, device="cuda", generator=g).bfloat16()
+    qk = torch.cat([q.reshape(S, 64), k.reshape(S, 64)], dim=1).contiguous()
+    vt = torch.zeros(H, 64, 1032, device="cuda", dtype=torch.bfloat16)
+    vt[:, :, :S] = v.permute(1, 2, 0)
+    out = torch.zeros(S, 64, device="cuda", dtype=torch.bfloat16)
+    ops.attention(qk, qk, vt, out, head_dim=64, heads=1, kv_heads=1, causal=False, scale=0.125, k_col0=64, nseq=1,
+                  seq_len=S)
+    ref = ref_attn(q.float(), k.float(), v.float(), False, 0.125)
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+def test_rowwise_kernels(ops, built_lib):
+    from mj_video_b200 import _lib, synth
+    from oracle import port
+    lib = built_lib
+    g = torch.Generator(device="cuda").manual_seed(3)
+    st = _lib.current_stream()
+    for rows, Cc in [(1000, 1024), (77, 128), (300, 4096), (5, 256)]:
+        x = torch.randn(rows, Cc, device="cuda", generator=g).bfloat16()
+        w = torch.randn(Cc, device="cuda", generator=g).bfloat16()
+        b = torch.randn(Cc, device="cuda", generator=g).bfloat16()
+        out = torch.empty_like(x)
+        _lib.check(lib.mjv_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), rows, Cc, 1e-6, st))
+        close(out, torch.nn.functional.layer_norm(x.float(), (Cc,), w.float(), b.float(), 1e-6).bfloat16(), ulps=1.5)
+        _lib.check(lib.mjv_rmsnorm(x.data_ptr(), w.data_ptr(), out.data_ptr(), rows, Cc, 1e-5, None, st))
+        xf = x.float()
+        ref = w * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).bfloat16()
+        close(out, ref, ulps=1.5)
+    # gathered rmsnorm (final norm on 2 rows per sample)
+    x = torch.randn(500, 2048, device="cuda", generator=g).bfloat16()
+    w = torch.randn(2048, device="cuda", generator=g).bfloat16()
+    idx = torch.tensor([3, 499, 0, 250], dtype=torch.int32, device="cuda")
+    out = torch.empty(4, 2048, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.mjv_rmsnorm(x.data_ptr(), w.data_ptr(), out.data_ptr(), 4, 2048, 1e-5, idx.data_ptr(), st))
+    xf = x[idx.long()].float()
+    close(out, w * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).bfloat16(), ulps=1.5)
+    # pixel-shuffle + LayerNorm against the oracle's own pixel_shuffle (modeling_internvl_chat.py:228-262)
+    T, S, Cv = 3, 1025, 128
+    hid = torch.randn(T, S, Cv, device="cuda", generator=g).bfloat16()
+    w = torch.randn(4 * Cv, device="cuda", generator=g).bfloat16()
+    b = torch.randn(4 * Cv, device="cuda", generator=g).bfloat16()
+    out = torch.empty(T * 256, 4 * Cv, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.mjv_pixel_shuffle_layernorm(hid.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), T, S, Cv,
+                                               1e-5, st))
+    orc = port.Oracle.__new__(port.Oracle)
+    ps = orc.pixel_shuffle(hid[:, 1:].float().reshape(T, 32, 32, Cv), 0.5).reshape(T * 256, 4 * Cv)
+    close(out, torch.nn.functional.layer_norm(ps, (4 * Cv,), w.float(), b.float(), 1e-5).bfloat16(), ulps=1.5)
+    # embedding gather skips <IMG_CONTEXT> rows
+    table = torch.randn(1000, 256, device="cuda", generator=g).bfloat16()
+    ids = torch.tensor([5, 999, 7, 7, 0], dtype=torch.int32, device="cuda")
+    out = torch.full((5, 256), 9.0, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.mjv_embed_tokens(ids.data_ptr(), table.data_ptr(), out.data_ptr(), 5, 256, 7, 1000, st))
+    assert torch.equal(out[[0, 1, 4]], table[[5, 999, 0]]) and (out[2:4] == 9.0).all()
+    # im2col == unfold of the conv operand (k = c*196 + ky*14 + kx), zero padded to 640
+    px = torch.randn(2, 3, 448, 448, device="cuda", generator=g)
+    for t, code in ((px, _lib.MJV_DTYPE_F32), (px.bfloat16(), _lib.MJV_DTYPE_BF16)):
+        out = torch.full((2 * 1024, 640), 7.0, device="cuda", dtype=torch.bfloat16)
+        _lib.check(lib.mjv_im2col_patches(t.contiguous().data_ptr(), code, out.data_ptr(), 2, 448, 14, 640, st))
+        ref = torch.nn.functional.unfold(t.float(), 14, stride=14).transpose(1, 2).reshape(2 * 1024, 588).bfloat16()
+        assert torch.equal(out[:, :588], ref) and (out[:, 588:] == 0).all()

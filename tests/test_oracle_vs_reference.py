@@ -1,0 +1,69 @@
+"""Pins the oracle against the reference ITSELF, imported unmodified from /root/reference (build container only)."""
+import pytest
+import torch
+
+from conftest import reference_available
+from mj_video_b200 import synth
+from oracle import port
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference is not present on this machine")
+
+
+@pytest.fixture(scope="module")
+def ref_model():
+    from oracle import reference_harness as rh
+    d = synth.dims_tiny()
+    sd = synth.make_state_dict(d, seed=3)
+    return d, sd, rh.build_reference_model(d, sd), rh
+
+
+def test_forward_bit_exact_fp32(ref_model):
+    d, sd, m, rh = ref_model
+    vids = [synth.make_video(3), synth.make_video(4)]
+    pv = torch.cat([rh.reference_load_video(v, num_segments=8, max_num=1)[0] for v in vids])
+    ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=46), synth.make_input_ids(1, [1] * 8, n_cap=20)])
+    ref = rh.reference_forward(m, pv, ids, mask)
+    out = port.Oracle(d, sd).forward(pv, ids, mask)
+    for k in ref:
+        assert torch.equal(ref[k].float(), out[k].float()), k
+
+
+def test_first_slot_layout(ref_model):
+    """All IMG_CONTEXT tokens in the first <image> slot (what the reference's own callers produce)."""
+    d, sd, m, rh = ref_model
+    pv = rh.reference_load_video(synth.make_video(9), num_segments=8, max_num=1)[0]
+    ids, mask = synth.pad_batch([synth.make_input_ids(5, [1] * 8, n_cap=30, first_slot_layout=True)])
+    ref = rh.reference_forward(m, pv, ids, mask)
+    out = port.Oracle(d, sd).forward(pv, ids, mask)
+    for k in ref:
+        assert torch.equal(ref[k].float(), out[k].float()), k
+
+
+def test_reference_errors(ref_model):
+    d, sd, m, rh = ref_model
+    pv = torch.zeros(8, 3, 448, 448)
+    ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=5)])
+    bad = ids.clone()
+    bad[0, -5:] = 7  # destroy the gating pattern
+    with pytest.raises(ValueError, match="Token pattern not found"):
+        rh.reference_forward(m, pv, bad, mask)
+    with pytest.raises(ValueError, match="Token pattern not found"):
+        port.Oracle(d, sd).forward(pv, bad, mask)
+
+
+@pytest.mark.parametrize("geom", [(896, 1344, 6), (1024, 1024, 6), (720, 1280, 6), (1280, 720, 6), (320, 512, 6),
+                                  (100, 77, 1), (500, 300, 4), (448, 448, 1)])
+def test_load_video_bit_exact(geom):
+    from oracle import reference_harness as rh
+    H, W, mx = geom
+    v = synth.make_video(7, n_frames=2, height=H, width=W)
+    a, c1 = rh.reference_load_video(v, num_segments=2, max_num=mx)
+    b, c2 = port.load_video_frames(v, num_segments=2, max_num=mx)
+    assert c1 == c2 and torch.equal(a, b)
+
+
+def test_get_index_matches():
+    from oracle import reference_harness as rh
+    mod = rh.reference_data_module()
+    for (bound, fps, mf, ns) in [(None, 8.0, 15, 8), (None, 30.0, 299, 32), ((1.0, 4.5), 24.0, 200, 16), (None, 8.0, 7, 8)]:
+        assert (mod.get_index(bound, fps, mf, 0, ns) == port.get_index(bound, fps, mf, 0, ns)).all()

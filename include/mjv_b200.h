@@ -84,6 +84,7 @@ typedef struct mjv_gemm_desc {
     int32_t vt_ld;
     int32_t seq;
     int32_t heads;
+    int32_t debug;        /* perf experiments only (0 in production)                 */
 } mjv_gemm_desc;
 
 int mjv_gemm_bf16(const mjv_gemm_desc* desc, void* stream);

@@ -5,11 +5,11 @@
 
 namespace mjv {
 
-template <int HD, int BKV, bool CAUSAL>
+template <int HD, bool CAUSAL>
 static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& a,
                          dim3 grid, cudaStream_t stream, double work) {
-    using L = attn_detail::Smem<HD, BKV>;
-    auto kfn = attention_kernel<HD, BKV, CAUSAL>;
+    using L = attn_detail::Smem<HD>;
+    auto kfn = attention_kernel<HD, CAUSAL>;
     static bool configured = false;
     if (!configured) {
         MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -31,7 +31,7 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     if (varlen) MJV_CHECK(d.work != nullptr && d.n_work > 0, MJV_ERR_ARG, "attention: varlen mode needs a work list");
     else MJV_CHECK(d.nseq > 0 && d.seq_len > 0, MJV_ERR_ARG, "attention: batched mode needs nseq/seq_len");
     const int hd = d.head_dim;
-    const int bkv = hd == 64 ? 128 : 64;
+    const int bkv = attn_detail::BKV;
 
     CUtensorMap tq, tk, tv;
     if (varlen) {
@@ -86,11 +86,11 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     else grid = dim3((unsigned)((d.seq_len + 127) / 128), (unsigned)d.heads, (unsigned)d.nseq);
 
     if (hd == 64) {
-        if (d.causal) return launch_attn_t<64, 128, true>(tq, tk, tv, a, grid, stream, work);
-        return launch_attn_t<64, 128, false>(tq, tk, tv, a, grid, stream, work);
+        if (d.causal) return launch_attn_t<64, true>(tq, tk, tv, a, grid, stream, work);
+        return launch_attn_t<64, false>(tq, tk, tv, a, grid, stream, work);
     }
-    if (d.causal) return launch_attn_t<128, 64, true>(tq, tk, tv, a, grid, stream, work);
-    return launch_attn_t<128, 64, false>(tq, tk, tv, a, grid, stream, work);
+    if (d.causal) return launch_attn_t<128, true>(tq, tk, tv, a, grid, stream, work);
+    return launch_attn_t<128, false>(tq, tk, tv, a, grid, stream, work);
 }
 
 }  // namespace mjv

@@ -6,7 +6,8 @@
 namespace mjv {
 
 template <int BN, int EPI, int STAGES>
-static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, cudaStream_t stream) {
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                         const CUtensorMap& tmO2, const GemmArgs& args, cudaStream_t stream) {
     using L = gemm_detail::SmemLayout<BN, STAGES>;
     auto kfn = gemm_bf16_tn_kernel<BN, EPI, STAGES>;
     static bool configured = false;  // per instantiation
@@ -18,23 +19,24 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
     const int grid = tiles < sm_count() ? tiles : sm_count();
     {
         LaunchScope scope(TAG_GEMM_STORE + EPI, stream, 2.0 * args.M * args.N * args.K);
-        kfn<<<grid, gemm_detail::kThreads, L::kTotal, stream>>>(tmA, tmB, args);
+        kfn<<<grid, gemm_detail::kThreads, L::kTotal, stream>>>(tmA, tmB, tmO, tmO2, args);
     }
     MJV_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 template <int BN, int STAGES>
-static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t s) {
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                        const CUtensorMap& tmO2, const GemmArgs& a, cudaStream_t s) {
     switch (epi) {
-        case EPI_STORE: return launch_gemm_t<BN, EPI_STORE, STAGES>(tmA, tmB, a, s);
-        case EPI_GELU: return launch_gemm_t<BN, EPI_GELU, STAGES>(tmA, tmB, a, s);
-        case EPI_RESID: return launch_gemm_t<BN, EPI_RESID, STAGES>(tmA, tmB, a, s);
-        case EPI_SWIGLU: return launch_gemm_t<BN, EPI_SWIGLU, STAGES>(tmA, tmB, a, s);
-        case EPI_QKV_LLM: return launch_gemm_t<BN, EPI_QKV_LLM, STAGES>(tmA, tmB, a, s);
-        case EPI_QKV_VIT: return launch_gemm_t<BN, EPI_QKV_VIT, STAGES>(tmA, tmB, a, s);
-        case EPI_PATCH: return launch_gemm_t<BN, EPI_PATCH, STAGES>(tmA, tmB, a, s);
-        case EPI_SCATTER: return launch_gemm_t<BN, EPI_SCATTER, STAGES>(tmA, tmB, a, s);
+        case EPI_STORE: return launch_gemm_t<BN, EPI_STORE, STAGES>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_GELU: return launch_gemm_t<BN, EPI_GELU, STAGES>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_RESID: return launch_gemm_t<BN, EPI_RESID, STAGES>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_SWIGLU: return launch_gemm_t<BN, EPI_SWIGLU, STAGES>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_QKV_LLM: return launch_gemm_t<BN, EPI_QKV_LLM, STAGES>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_QKV_VIT: return launch_gemm_t<BN, EPI_QKV_VIT, STAGES>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_PATCH: return launch_gemm_t<BN, EPI_PATCH, STAGES>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_SCATTER: return launch_gemm_t<BN, EPI_SCATTER, STAGES>(tmA, tmB, tmO, tmO2, a, s);
         default: return set_error(MJV_ERR_ARG, "unknown GEMM epilogue %d", epi);
     }
 }
@@ -90,9 +92,27 @@ int gemm_bf16(const mjv_gemm_desc& d, cudaStream_t stream) {
     a.vt_ld = d.vt_ld;
     a.seq = d.seq;
     a.heads = d.heads;
+    a.debug = d.debug;
 
-    if (bn == 256) return dispatch_epi<256, 4>(d.epilogue, tmA, tmB, a, stream);
-    return dispatch_epi<128, 6>(d.epilogue, tmA, tmB, a, stream);
+    // output tensor maps for the TMA-store epilogue (BN == 256): [32 rows x 64 columns] boxes, 128B swizzle
+    CUtensorMap tmO, tmO2;
+    memset(&tmO, 0, sizeof(tmO));
+    memset(&tmO2, 0, sizeof(tmO2));
+    if (bn == 256 && d.epilogue != EPI_SCATTER) {
+        uint64_t rows = (uint64_t)d.M, cols = (uint64_t)d.N;
+        if (d.epilogue == EPI_SWIGLU) cols = (uint64_t)d.N / 2;
+        if (d.epilogue == EPI_PATCH) rows = (uint64_t)d.M + (uint64_t)d.M / (uint64_t)d.seq;
+        if (d.epilogue == EPI_QKV_VIT) cols = (uint64_t)(d.n_q_cols + d.n_k_cols);
+        if (d.epilogue == EPI_QKV_LLM) cols = (uint64_t)d.n_q_cols;
+        MJV_CHECK(d.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0, MJV_ERR_ARG,
+                  "gemm: output must be 16-byte aligned with ldo a multiple of 8");
+        MJV_PROPAGATE(make_tmap_2d(&tmO, d.out, rows, cols, (uint64_t)d.ldo, 32));
+        if (d.epilogue == EPI_QKV_LLM)
+            MJV_PROPAGATE(make_tmap_2d(&tmO2, d.out_k, rows, (uint64_t)d.n_k_cols, (uint64_t)d.n_k_cols, 32));
+        if (d.epilogue == EPI_PATCH) MJV_CHECK(d.seq % 32 == 0, MJV_ERR_ARG, "gemm: PATCH needs seq %% 32 == 0");
+    }
+    if (bn == 256) return dispatch_epi<256, 4>(d.epilogue, tmA, tmB, tmO, tmO2, a, stream);
+    return dispatch_epi<128, 6>(d.epilogue, tmA, tmB, tmO, tmO2, a, stream);
 }
 
 }  // namespace mjv

@@ -3,7 +3,8 @@
 //   * A (activations) and W (nn.Linear weight, [out,in]) are both K-major, loaded by TMA into 128B-swizzled
 //     shared-memory stages; tcgen05.mma (cta_group::1, M=128, N=BN, K=16) accumulates fp32 in TMEM.
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM allocator,
-//     warps 4..7 = epilogue (TMEM -> registers -> fused math -> global).
+//     warps 4..11 = epilogue (TMEM -> registers -> fused math -> global): two warps per TMEM lane quarter, each
+//     taking half of the tile's columns, so every SM sub-partition has two epilogue warps to hide latency.
 //   * two TMEM accumulator buffers (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 //   * static persistent schedule: tile = blockIdx.x + i * gridDim.x, n-fastest so co-resident CTAs share A rows
 //     and the whole W stays L2-resident.
@@ -51,13 +52,15 @@ struct GemmArgs {
     int vt_ld;                 // QKV: row stride of V^T (padded token count)
     int seq;                   // QKV_VIT: tokens per tile (1025); PATCH: patches per tile (1024)
     int heads;                 // QKV_VIT: heads
+    int debug;                 // perf experiments only: 1 = epilogue skips TMEM loads and stores, 2 = loads but no stores
 };
 
 namespace gemm_detail {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
 
 __device__ __forceinline__ float gelu_erf(float x) {
     // 0.5*x*(1+erf(x/sqrt2)); erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution)
@@ -90,12 +93,16 @@ __device__ __forceinline__ void store32_bf16(__nv_bfloat16* p, const uint32_t* u
     for (int i = 0; i < 4; ++i) q[i] = make_uint4(u[4 * i + 0], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
 }
 
+constexpr int kStagingBytesPerWarp = 32 * 128;  // [32 rows][64 bf16] swizzled tile for one TMA store
+
 template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr bool kTmaStore = (BN == 256);  // 64-column output boxes per epilogue warp need BN/2 >= 128
+    static constexpr int kStagingOffset = STAGES * kStageBytes;
+    static constexpr int kBarOffset = kStagingOffset + (kTmaStore ? kEpiWarps * kStagingBytesPerWarp : 0);
     static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
@@ -104,6 +111,7 @@ struct SmemLayout {
 template <int BN, int EPI, int STAGES>
 __global__ void __launch_bounds__(gemm_detail::kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
                     const GemmArgs args) {
     using namespace gemm_detail;
     using L = SmemLayout<BN, STAGES>;
@@ -133,7 +141,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
-            ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+            ptx::mbar_init(&tmem_empty[a], kEpiWarps);  // one arrive per epilogue warp
         }
         ptx::fence_barrier_init();
     }
@@ -200,8 +208,35 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else if (warp >= 4) {
-        // ===================================================== epilogue (warp%4 selects the TMEM lane quarter)
+        // ===================================================== epilogue (warp%4 selects the TMEM lane quarter,
+        // (warp-4)/4 the column half). With BN == 256 results leave through a per-warp swizzled staging tile and a TMA
+        // bulk store ([32 rows x 64 columns] boxes); per-thread row-strided global stores cost up to 40% of the kernel.
         const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        constexpr int HB = BN / 2;
+        constexpr bool kTma = L::kTmaStore;
+        const int c_begin = half * HB;
+        const int c_end = c_begin + HB;
+        uint8_t* stg = smem + L::kStagingOffset + (warp - 4) * kStagingBytesPerWarp;
+        auto stg_wait = [&]() {  // the previous bulk store has finished reading the staging tile
+            if (lane == 0) ptx::bulk_wait_read0();
+            __syncwarp();
+        };
+        auto stg_put = [&](int hc, const uint32_t* o) {  // 32 columns (16 packed pairs) of this thread's row
+            uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                *reinterpret_cast<uint4*>(rowp + (((hc * 4 + g) ^ (lane & 7)) * 16)) =
+                    make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+        };
+        auto stg_store = [&](const CUtensorMap* tm, int col, int row) {
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                ptx::tma_store_2d(tm, stg, col, row);
+                ptx::bulk_commit();
+            }
+        };
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -216,17 +251,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_RESID || EPI == EPI_PATCH ||
                           EPI == EPI_SCATTER) {
                 long long orow = row;
+                int orow0 = m0 + q * 32;  // first output row of this warp's 32-row group (TMA store)
                 int prow = 0;
                 if constexpr (EPI == EPI_PATCH) {
                     orow = row + row / args.seq + 1;
+                    orow0 = m0 + q * 32 + (m0 + q * 32) / args.seq + 1;  // 32-row groups never straddle two images
                     prow = row % args.seq + 1;
                 }
                 if constexpr (EPI == EPI_SCATTER) orow = row_ok ? args.row_map[row] : 0;
+                constexpr bool tma_out = kTma && EPI != EPI_SCATTER;
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = c_begin; c < c_end; c += 32) {
+                    if (args.debug == 1) break;
+                    const int hc = ((c - c_begin) >> 5) & 1;
+                    if (tma_out && hc == 0) stg_wait();
                     uint32_t v[32];
                     ptx::tmem_ld_x32(t_base + c, v);
                     ptx::tmem_wait_ld();
+                    if (args.debug == 2) {
+                        if (v[0] == 0x7fc12345u) args.out[0] = __float2bfloat16_rn(1.f);  // keep the load alive
+                        continue;
+                    }
                     const int n = n0 + c;
                     uint32_t o[16];
                     uint32_t b[16];
@@ -236,79 +281,103 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 16; ++i) b[i] = 0u;
                     }
+                    uint32_t r[16], s[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = s[i] = 0u;
                     if (row_ok) {
-                        uint32_t r[16], s[16];
                         if constexpr (EPI == EPI_RESID) {
                             load32_bf16(args.residual + static_cast<long long>(row) * args.ldr + n, r);
                             if (args.scale != nullptr) load32_bf16(args.scale + n, s);
                         }
                         if constexpr (EPI == EPI_PATCH) load32_bf16(args.pos + static_cast<long long>(prow) * args.N + n, r);
+                    }
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float x0 = ptx::bf16_round(__uint_as_float(v[2 * i]) + ptx::bf16_lo(b[i]));
-                            float x1 = ptx::bf16_round(__uint_as_float(v[2 * i + 1]) + ptx::bf16_hi(b[i]));
-                            if constexpr (EPI == EPI_GELU) {
-                                x0 = gelu_erf(x0);
-                                x1 = gelu_erf(x1);
-                            }
-                            if constexpr (EPI == EPI_RESID) {
-                                if (args.scale != nullptr) {
-                                    x0 = ptx::bf16_round(x0 * ptx::bf16_lo(s[i]));
-                                    x1 = ptx::bf16_round(x1 * ptx::bf16_hi(s[i]));
-                                }
-                                x0 += ptx::bf16_lo(r[i]);
-                                x1 += ptx::bf16_hi(r[i]);
-                            }
-                            if constexpr (EPI == EPI_PATCH) {
-                                x0 += ptx::bf16_lo(r[i]);
-                                x1 += ptx::bf16_hi(r[i]);
-                            }
-                            o[i] = ptx::pack_bf16x2(x0, x1);
+                    for (int i = 0; i < 16; ++i) {
+                        float x0 = ptx::bf16_round(__uint_as_float(v[2 * i]) + ptx::bf16_lo(b[i]));
+                        float x1 = ptx::bf16_round(__uint_as_float(v[2 * i + 1]) + ptx::bf16_hi(b[i]));
+                        if constexpr (EPI == EPI_GELU) {
+                            x0 = gelu_erf(x0);
+                            x1 = gelu_erf(x1);
                         }
-                        store32_bf16(args.out + orow * args.ldo + n, o);
+                        if constexpr (EPI == EPI_RESID) {
+                            if (args.scale != nullptr) {
+                                x0 = ptx::bf16_round(x0 * ptx::bf16_lo(s[i]));
+                                x1 = ptx::bf16_round(x1 * ptx::bf16_hi(s[i]));
+                            }
+                            x0 += ptx::bf16_lo(r[i]);
+                            x1 += ptx::bf16_hi(r[i]);
+                        }
+                        if constexpr (EPI == EPI_PATCH) {
+                            x0 += ptx::bf16_lo(r[i]);
+                            x1 += ptx::bf16_hi(r[i]);
+                        }
+                        o[i] = ptx::pack_bf16x2(x0, x1);
+                    }
+                    if constexpr (tma_out) {
+                        stg_put(hc, o);
+                        if (hc == 1) stg_store(&tmO, n - 32, orow0);
+                    } else {
+                        if (row_ok) store32_bf16(args.out + orow * args.ldo + n, o);
                     }
                 }
             } else if constexpr (EPI == EPI_SWIGLU) {
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 64) {
+                for (int c = c_begin; c < c_end; c += 64) {
+                    const int hc = ((c - c_begin) >> 6) & 1;
+                    if (kTma && hc == 0) stg_wait();
                     uint32_t g[32], u[32];
                     ptx::tmem_ld_x32(t_base + c, g);
                     ptx::tmem_ld_x32(t_base + c + 32, u);
                     ptx::tmem_wait_ld();
-                    if (row_ok) {
-                        uint32_t o[16];
+                    uint32_t o[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float g0 = ptx::bf16_round(__uint_as_float(g[2 * i]));
-                            const float g1 = ptx::bf16_round(__uint_as_float(g[2 * i + 1]));
-                            const float u0 = ptx::bf16_round(__uint_as_float(u[2 * i]));
-                            const float u1 = ptx::bf16_round(__uint_as_float(u[2 * i + 1]));
-                            o[i] = ptx::pack_bf16x2(ptx::bf16_round(silu(g0)) * u0, ptx::bf16_round(silu(g1)) * u1);
-                        }
-                        store32_bf16(args.out + static_cast<long long>(row) * args.ldo + ((n0 + c) >> 1), o);
+                    for (int i = 0; i < 16; ++i) {
+                        const float g0 = ptx::bf16_round(__uint_as_float(g[2 * i]));
+                        const float g1 = ptx::bf16_round(__uint_as_float(g[2 * i + 1]));
+                        const float u0 = ptx::bf16_round(__uint_as_float(u[2 * i]));
+                        const float u1 = ptx::bf16_round(__uint_as_float(u[2 * i + 1]));
+                        o[i] = ptx::pack_bf16x2(ptx::bf16_round(silu(g0)) * u0, ptx::bf16_round(silu(g1)) * u1);
+                    }
+                    if constexpr (kTma) {
+                        stg_put(hc, o);
+                        if (hc == 1) stg_store(&tmO, (n0 + c_begin) >> 1, m0 + q * 32);
+                    } else {
+                        if (row_ok) store32_bf16(args.out + static_cast<long long>(row) * args.ldo + ((n0 + c) >> 1), o);
                     }
                 }
             } else if constexpr (EPI == EPI_QKV_LLM) {
-                // head_dim 128: rotate-half pairs column j with j+64, i.e. chunk c with chunk c+2.
+                // head_dim 128: rotate-half pairs column j with j+64, i.e. 32-column chunk c with chunk c+2.
                 const int pos = row_ok ? args.row_pos[row] : 0;
+                // BN == 256: this warp owns head `half` of the tile; BN == 128: the two halves share the single head
+                constexpr int kHeadsPerTile = BN / 128;
 #pragma unroll 1
-                for (int h0 = 0; h0 < BN; h0 += 128) {
+                for (int hh = 0; hh < kHeadsPerTile; ++hh) {
+                    if (kTma && hh != half) continue;
+                    const int h0 = hh * 128;
                     const int n = n0 + h0;  // first column of this head
                     if (n < args.n_q_cols + args.n_k_cols) {
                         const bool is_q = n < args.n_q_cols;
+                        const int ncol = is_q ? n : n - args.n_q_cols;
                         __nv_bfloat16* dst =
                             is_q ? args.out + static_cast<long long>(row) * args.ldo + n
                                  : args.out_k + static_cast<long long>(row) * args.n_k_cols + (n - args.n_q_cols);
-#pragma unroll 1
-                        for (int c = 0; c < 64; c += 32) {
+                        const CUtensorMap* tm = is_q ? &tmO : &tmO2;
+                        uint32_t hi_keep[2][16];  // rotated second halves (columns 64..127), stored after the first box
+#pragma unroll
+                        for (int cp = 0; cp < 2; ++cp) {
+                            if (!kTma && cp != half) continue;  // BN == 128: each half does one rope pair
+                            const int c = cp * 32;
+                            if (kTma && cp == 0) stg_wait();
                             uint32_t x1[32], x2[32];
                             ptx::tmem_ld_x32(t_base + h0 + c, x1);
                             ptx::tmem_ld_x32(t_base + h0 + c + 64, x2);
                             ptx::tmem_wait_ld();
+                            uint32_t o1[16], o2[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o1[i] = o2[i] = 0u;
                             if (row_ok) {
                                 const float4* cs = reinterpret_cast<const float4*>(args.rope_cos + static_cast<long long>(pos) * 64 + c);
                                 const float4* sn = reinterpret_cast<const float4*>(args.rope_sin + static_cast<long long>(pos) * 64 + c);
-                                uint32_t o1[16], o2[16];
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     const float4 cv = __ldg(cs + i);
@@ -329,17 +398,34 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     o2[2 * i] = ptx::pack_bf16x2(b[0], b[1]);
                                     o2[2 * i + 1] = ptx::pack_bf16x2(b[2], b[3]);
                                 }
-                                store32_bf16(dst + c, o1);
-                                store32_bf16(dst + c + 64, o2);
                             }
+                            if constexpr (kTma) {
+                                stg_put(cp, o1);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) hi_keep[cp][i] = o2[i];
+                            } else {
+                                if (row_ok) {
+                                    store32_bf16(dst + c, o1);
+                                    store32_bf16(dst + c + 64, o2);
+                                }
+                            }
+                        }
+                        if constexpr (kTma) {
+                            stg_store(tm, ncol, m0 + q * 32);       // columns 0..63 of the head
+                            stg_wait();
+                            stg_put(0, hi_keep[0]);
+                            stg_put(1, hi_keep[1]);
+                            stg_store(tm, ncol + 64, m0 + q * 32);  // columns 64..127
                         }
                     } else {
                         // V head: transposed store, V^T[head][d][token]
                         const int vcol = n - args.n_q_cols - args.n_k_cols;  // head*128
                         const int vtc = (row_ok && args.row_vt != nullptr) ? args.row_vt[row] : row;
                         __nv_bfloat16* dst = args.out_vt + static_cast<long long>(vcol >> 7) * args.vt_stride_head + vtc;
+                        const int cb = kTma ? 0 : half * 64;
+                        const int ce = kTma ? 128 : half * 64 + 64;
 #pragma unroll 1
-                        for (int c = 0; c < 128; c += 32) {
+                        for (int c = cb; c < ce; c += 32) {
                             uint32_t v[32];
                             ptx::tmem_ld_x32(t_base + h0 + c, v);
                             ptx::tmem_wait_ld();
@@ -354,36 +440,42 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             } else if constexpr (EPI == EPI_QKV_VIT) {
                 const int t = row / args.seq;
                 const int s = row - t * args.seq;
+                const bool qk_tile = n0 < args.n_q_cols + args.n_k_cols;  // tiles never straddle the k|v boundary
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = c_begin; c < c_end; c += 32) {
+                    const int hc = ((c - c_begin) >> 5) & 1;
+                    if (kTma && qk_tile && hc == 0) stg_wait();
                     uint32_t v[32];
                     ptx::tmem_ld_x32(t_base + c, v);
                     ptx::tmem_wait_ld();
                     const int n = n0 + c;
                     uint32_t b[16];
                     load32_bf16(args.bias + n, b);
-                    if (row_ok) {
-                        if (n < args.n_q_cols + args.n_k_cols) {
-                            uint32_t o[16];
+                    if (n < args.n_q_cols + args.n_k_cols) {
+                        uint32_t o[16];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                o[i] = ptx::pack_bf16x2(__uint_as_float(v[2 * i]) + ptx::bf16_lo(b[i]),
-                                                        __uint_as_float(v[2 * i + 1]) + ptx::bf16_hi(b[i]));
-                            store32_bf16(args.out + static_cast<long long>(row) * args.ldo + n, o);
+                        for (int i = 0; i < 16; ++i)
+                            o[i] = ptx::pack_bf16x2(__uint_as_float(v[2 * i]) + ptx::bf16_lo(b[i]),
+                                                    __uint_as_float(v[2 * i + 1]) + ptx::bf16_hi(b[i]));
+                        if constexpr (kTma) {
+                            stg_put(hc, o);
+                            if (hc == 1) stg_store(&tmO, n - 32, m0 + q * 32);
                         } else {
-                            const int vcol = n - args.n_q_cols - args.n_k_cols;  // head*64 + d
-                            const int head = vcol >> 6;
-                            const int d0 = vcol & 63;
-                            __nv_bfloat16* dst = args.out_vt +
-                                                 (static_cast<long long>(t) * args.heads + head) * args.vt_stride_head +
-                                                 static_cast<long long>(d0) * args.vt_ld + s;
+                            if (row_ok) store32_bf16(args.out + static_cast<long long>(row) * args.ldo + n, o);
+                        }
+                    } else if (row_ok) {
+                        const int vcol = n - args.n_q_cols - args.n_k_cols;  // head*64 + d
+                        const int head = vcol >> 6;
+                        const int d0 = vcol & 63;
+                        __nv_bfloat16* dst = args.out_vt +
+                                             (static_cast<long long>(t) * args.heads + head) * args.vt_stride_head +
+                                             static_cast<long long>(d0) * args.vt_ld + s;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                dst[static_cast<long long>(2 * i) * args.vt_ld] =
-                                    __float2bfloat16_rn(__uint_as_float(v[2 * i]) + ptx::bf16_lo(b[i]));
-                                dst[static_cast<long long>(2 * i + 1) * args.vt_ld] =
-                                    __float2bfloat16_rn(__uint_as_float(v[2 * i + 1]) + ptx::bf16_hi(b[i]));
-                            }
+                        for (int i = 0; i < 16; ++i) {
+                            dst[static_cast<long long>(2 * i) * args.vt_ld] =
+                                __float2bfloat16_rn(__uint_as_float(v[2 * i]) + ptx::bf16_lo(b[i]));
+                            dst[static_cast<long long>(2 * i + 1) * args.vt_ld] =
+                                __float2bfloat16_rn(__uint_as_float(v[2 * i + 1]) + ptx::bf16_hi(b[i]));
                         }
                     }
                 }
@@ -395,6 +487,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (kTma && lane == 0) ptx::bulk_wait0();  // all bulk stores of this warp have landed before the CTA exits
     }
 
     ptx::tc_fence_before();

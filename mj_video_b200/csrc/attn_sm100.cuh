@@ -6,9 +6,10 @@
 // One CTA = one (sequence, head, 128-query block); KV blocks of 64. Software-pipelined over KV blocks j:
 //   MMA thread : S_{j+1} = Q·K_{j+1}ᵀ is issued BEFORE waiting for P_j (S is double-buffered in TMEM)  -> s_full[b]
 //   softmax    : 128 threads, one query row each (TMEM lane == row): ONE tcgen05.ld pass brings the 64 scores of the
-//                row into registers (TMEM read bandwidth is the scarce resource), row max, p = exp2(s·c − m) with
-//                packed fp32x2 math, P written as bf16 into a 128B-swizzled K-major smem tile          -> p_full
-//   MMA thread : O += P_j·V_j (A = P from smem, B = Vᵀ tile from smem, accumulator stays in TMEM)     -> pv_done, kv_empty
+//                row into registers, row max, p = exp2(s·c − m) with packed fp32x2 math; P (bf16) is written BACK INTO
+//                TMEM over the S buffer it came from (tcgen05.st), one barrier arrival per warp        -> p_full
+//   MMA thread : O += P_j·V_j (A = P from TMEM, B = Vᵀ tile from smem, accumulator stays in TMEM)     -> pv_done, kv_empty
+//                (tcgen05.mma executes in issue order, so S_{j+2} cannot overwrite P_j before P_j·V_j has read it)
 // so the softmax of block j+1 starts as soon as block j's P is handed over, while P_j·V_j runs on the tensor pipe.
 // The output accumulator never leaves TMEM until the end; the running max is updated lazily (only when it grows by more
 // than 2^8), in which case O is rescaled in place with tcgen05.ld/st after waiting for the P·V in flight (pv_done).
@@ -47,12 +48,10 @@ struct Smem {
     static constexpr int kQBytes = BQ * HD * 2;
     static constexpr int kKBytes = BKV * HD * 2;
     static constexpr int kVBytes = HD * BKV * 2;
-    static constexpr int kPBytes = BQ * BKV * 2;
     static constexpr int kQOff = 0;
     static constexpr int kKOff = kQOff + kQBytes;
     static constexpr int kVOff = kKOff + kStages * kKBytes;
-    static constexpr int kPOff = kVOff + kStages * kVBytes;
-    static constexpr int kBarOff = kPOff + kPBytes;
+    static constexpr int kBarOff = kVOff + kStages * kVBytes;
     static constexpr int kTotal = kBarOff + 256;
 };
 }  // namespace attn_detail
@@ -68,7 +67,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint8_t* sQ = smem + L::kQOff;
     uint8_t* sK = smem + L::kKOff;
     uint8_t* sV = smem + L::kVOff;
-    uint8_t* sP = smem + L::kPOff;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
     uint64_t* q_full = bars + 0;
     uint64_t* k_full = bars + 1;         // [ST]
@@ -77,7 +75,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint64_t* s_full = bars + 1 + 3 * ST;    // [2]
     uint64_t* p_full = s_full + 2;
     uint64_t* pv_done = s_full + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
+    uint64_t* o_done = s_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -128,8 +127,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         ptx::mbar_init(&s_full[0], 1);
         ptx::mbar_init(&s_full[1], 1);
-        ptx::mbar_init(p_full, 128);
+        ptx::mbar_init(p_full, 4);  // one arrival per softmax warp
         ptx::mbar_init(pv_done, 1);
+        ptx::mbar_init(o_done, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -174,7 +174,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
             constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD);
             const uint32_t q_addr = ptx::smem_u32(sQ);
-            const uint32_t p_addr = ptx::smem_u32(sP);
             auto issue_s = [&](int jj, int stage) {
                 const uint32_t k_addr = ptx::smem_u32(sK + stage * L::kKBytes);
                 const uint32_t d = tmem_base + (jj & 1) * BKV;
@@ -211,16 +210,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const uint32_t v_addr = ptx::smem_u32(sV + st * L::kVBytes);
                 const int valid = min(BKV, kv_end - j * BKV);
                 const int ksteps = (valid + 15) >> 4;
+                const uint32_t p_tmem = tmem_base + (j & 1) * BKV;  // P_j lives in the first 32 columns of S buffer j&1
                 for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint64_t a = ptx::make_desc_sw128(p_addr + ks * 32);
                     const uint64_t b = ptx::make_desc_sw128(v_addr + ks * 32);
-                    ptx::mma_bf16_ss(tmem_O, a, b, idesc_o, (j | ks) != 0 ? 1u : 0u);
+                    ptx::mma_bf16_ts(tmem_O, p_tmem + ks * 8, b, idesc_o, (j | ks) != 0 ? 1u : 0u);
                 }
                 ptx::mma_commit(&kv_empty[st]);
                 ptx::mma_commit(pv_done);
                 st = st1;
                 ph = ph1;
             }
+            // pv_done alternates phases every block, so a parity wait on it can alias when a warp races through its last
+            // (masked) steps; the final hand-over gets its own single-phase barrier
+            ptx::mma_commit(o_done);
         }
     } else if (warp >= 4) {
         // ===================================================== softmax / output (TMEM lane == query row)
@@ -231,16 +233,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t lane_sel = static_cast<uint32_t>(qw * 32) << 16;
         float m_run = -INFINITY;
         float l_run = 0.0f;
-        uint8_t* p_row = sP + r * 128;
-        const int swz = r & 7;
 
         for (int j = 0; j < n_blocks; ++j) {
+            // a warp with nothing to do (no valid rows / causally masked) must not lap the others: its arrival for step
+            // j may only be counted once phase j-1 of p_full has completed
+            if (j > 0) ptx::mbar_wait(p_full, (j - 1) & 1);
             ptx::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t tmem_S = tmem_base + (j & 1) * BKV + lane_sel;
             const int kv0 = j * BKV;
             const int valid = min(BKV, kv_end - kv0);  // columns of this block that exist (block level)
-            const int nchunks = (valid + 31) >> 5;     // 32-column chunks the P·V MMA may read
             int lim = valid;                           // per-row column limit (exclusive, block-relative)
             if (CAUSAL) lim = min(valid, qrow - kv0 + 1);
             const bool warp_masked = CAUSAL && (kv0 > q0 + qw * 32 + 31);  // every row of this warp sees nothing here
@@ -333,30 +335,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 for (int i = 0; i < 32; ++i) v[i] = 0u;
                 write_p = true;
             }
-            // the single P tile is free once P·V_{j-1} has retired (normally long ago: it ran during this softmax)
-            if (j > 0) ptx::mbar_wait(pv_done, (j - 1) & 1);
+            // P_j (bf16 pairs, 32 columns) overwrites the scores it was computed from
             if (write_p) {
-                // 128B swizzle: 16-byte chunk index ^= row & 7
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (c < nchunks) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const int chunk16 = (c * 4 + g) ^ swz;
-                            *reinterpret_cast<uint4*>(p_row + chunk16 * 16) =
-                                make_uint4(v[c * 16 + 4 * g], v[c * 16 + 4 * g + 1], v[c * 16 + 4 * g + 2],
-                                           v[c * 16 + 4 * g + 3]);
-                        }
-                    }
-                }
+                ptx::tmem_st_x32(tmem_S, v);
+                ptx::tmem_wait_st();
             }
-            ptx::fence_proxy_async_smem();
             ptx::tc_fence_before();
-            ptx::mbar_arrive(p_full);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(p_full);
         }
 
         // ---- epilogue: O / l -> bf16
-        ptx::mbar_wait(pv_done, (n_blocks - 1) & 1);
+        ptx::mbar_wait(o_done, 0);
         ptx::tc_fence_after();
         if (warp_has_rows) {
             const float inv = 1.0f / l_run;

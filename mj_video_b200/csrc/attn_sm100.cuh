@@ -235,9 +235,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         float l_run = 0.0f;
 
         for (int j = 0; j < n_blocks; ++j) {
-            // a warp with nothing to do (no valid rows / causally masked) must not lap the others: its arrival for step
-            // j may only be counted once phase j-1 of p_full has completed
-            if (j > 0) ptx::mbar_wait(p_full, (j - 1) & 1);
             ptx::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t tmem_S = tmem_base + (j & 1) * BKV + lane_sel;
@@ -342,7 +339,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(p_full);
+            // A warp with little to do (no valid rows / causally masked) must not lap the others: its arrival for step j
+            // may only be counted once phase j-1 of p_full has completed. Checked here, after the work, so that busy
+            // warps (for which the phase completed long ago) never stall on it and do not run in lock-step.
+            if (lane == 0) {
+                if (j > 0) ptx::mbar_wait(p_full, (j - 1) & 1);
+                ptx::mbar_arrive(p_full);
+            }
+            __syncwarp();
         }
 
         // ---- epilogue: O / l -> bf16

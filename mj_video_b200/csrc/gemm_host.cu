@@ -110,6 +110,11 @@ int gemm_bf16(const mjv_gemm_desc& d, cudaStream_t stream) {
         if (d.epilogue == EPI_QKV_LLM)
             MJV_PROPAGATE(make_tmap_2d(&tmO2, d.out_k, rows, (uint64_t)d.n_k_cols, (uint64_t)d.n_k_cols, 32));
         if (d.epilogue == EPI_PATCH) MJV_CHECK(d.seq % 32 == 0, MJV_ERR_ARG, "gemm: PATCH needs seq %% 32 == 0");
+        if (d.epilogue == EPI_RESID) {
+            MJV_CHECK(d.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0, MJV_ERR_ARG,
+                      "gemm: residual must be 16-byte aligned with ldr a multiple of 8");
+            MJV_PROPAGATE(make_tmap_2d(&tmO2, d.residual, rows, cols, (uint64_t)d.ldr, 32));
+        }
     }
     if (bn == 256) return dispatch_epi<256, 4>(d.epilogue, tmA, tmB, tmO, tmO2, a, stream);
     return dispatch_epi<128, 6>(d.epilogue, tmA, tmB, tmO, tmO2, a, stream);

@@ -123,7 +123,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_bar = tmem_empty + 2;  // [kEpiWarps] residual-tile TMA loads, one barrier per epilogue warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -143,6 +144,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::mbar_init(&tmem_full[a], 1);
             ptx::mbar_init(&tmem_empty[a], kEpiWarps);  // one arrive per epilogue warp
         }
+        for (int w = 0; w < kEpiWarps; ++w) ptx::mbar_init(&res_bar[w], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -239,6 +241,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         };
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint32_t res_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / args.num_n_blocks) * BM;
             const int n0 = (tile % args.num_n_blocks) * BN;
@@ -260,11 +263,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 if constexpr (EPI == EPI_SCATTER) orow = row_ok ? args.row_map[row] : 0;
                 constexpr bool tma_out = kTma && EPI != EPI_SCATTER;
+                constexpr bool tma_res = tma_out && EPI == EPI_RESID;  // residual tile arrives by TMA into the staging tile
 #pragma unroll 1
                 for (int c = c_begin; c < c_end; c += 32) {
                     if (args.debug == 1) break;
                     const int hc = ((c - c_begin) >> 5) & 1;
-                    if (tma_out && hc == 0) stg_wait();
+                    if (tma_out && hc == 0) {
+                        stg_wait();
+                        if (tma_res && lane == 0) {
+                            ptx::mbar_expect_tx(&res_bar[warp - 4], kStagingBytesPerWarp);
+                            ptx::tma_load_2d(stg, &tmO2, &res_bar[warp - 4], n0 + c, orow0, ptx::kEvictFirst);
+                        }
+                    }
                     uint32_t v[32];
                     ptx::tmem_ld_x32(t_base + c, v);
                     ptx::tmem_wait_ld();
@@ -284,8 +294,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     uint32_t r[16], s[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) r[i] = s[i] = 0u;
+                    if constexpr (tma_res) {
+                        if (args.scale != nullptr) load32_bf16(args.scale + n, s);
+                        if (hc == 0) {
+                            ptx::mbar_wait(&res_bar[warp - 4], res_phase);
+                            res_phase ^= 1;
+                        }
+                        const uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint4 t4 = *reinterpret_cast<const uint4*>(rowp + (((hc * 4 + g) ^ (lane & 7)) * 16));
+                            r[4 * g] = t4.x;
+                            r[4 * g + 1] = t4.y;
+                            r[4 * g + 2] = t4.z;
+                            r[4 * g + 3] = t4.w;
+                        }
+                    }
                     if (row_ok) {
-                        if constexpr (EPI == EPI_RESID) {
+                        if constexpr (EPI == EPI_RESID && !tma_res) {
                             load32_bf16(args.residual + static_cast<long long>(row) * args.ldr + n, r);
                             if (args.scale != nullptr) load32_bf16(args.scale + n, s);
                         }

@@ -85,6 +85,7 @@ typedef struct mjv_gemm_desc {
     int32_t seq;
     int32_t heads;
     int32_t debug;        /* perf experiments only (0 in production)                 */
+    int32_t cta_group;    /* 0 = auto (CTA pairs when block_n = 256), 1 or 2         */
 } mjv_gemm_desc;
 
 int mjv_gemm_bf16(const mjv_gemm_desc* desc, void* stream);

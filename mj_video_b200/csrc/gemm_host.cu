@@ -1,42 +1,62 @@
 // Host launcher for the tcgen05 GEMM family (see gemm_sm100.cuh).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm_sm100.cuh"
 #include "launch.cuh"
 
 namespace mjv {
 
-template <int BN, int EPI, int STAGES>
+template <int BN, int EPI, int STAGES, int CG>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                          const CUtensorMap& tmO2, const GemmArgs& args, cudaStream_t stream) {
-    using L = gemm_detail::SmemLayout<BN, STAGES>;
-    auto kfn = gemm_bf16_tn_kernel<BN, EPI, STAGES>;
+    using L = gemm_detail::SmemLayout<BN, STAGES, CG>;
+    auto kfn = gemm_bf16_tn_kernel<BN, EPI, STAGES, CG>;
     static bool configured = false;  // per instantiation
     if (!configured) {
         MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         configured = true;
     }
     const int tiles = args.num_m_blocks * args.num_n_blocks;
-    const int grid = tiles < sm_count() ? tiles : sm_count();
+    const int max_groups = sm_count() / CG;
+    const int groups = tiles < max_groups ? tiles : max_groups;
     {
         LaunchScope scope(TAG_GEMM_STORE + EPI, stream, 2.0 * args.M * args.N * args.K);
-        kfn<<<grid, gemm_detail::kThreads, L::kTotal, stream>>>(tmA, tmB, tmO, tmO2, args);
+        if constexpr (CG == 1) {
+            kfn<<<groups, gemm_detail::kThreads, L::kTotal, stream>>>(tmA, tmB, tmO, tmO2, args);
+        } else {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(groups * CG);
+            cfg.blockDim = dim3(gemm_detail::kThreads);
+            cfg.dynamicSmemBytes = L::kTotal;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = CG;
+            attr.val.clusterDim.y = 1;
+            attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            MJV_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, tmO, tmO2, args));
+        }
     }
     MJV_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG>
 static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                         const CUtensorMap& tmO2, const GemmArgs& a, cudaStream_t s) {
     switch (epi) {
-        case EPI_STORE: return launch_gemm_t<BN, EPI_STORE, STAGES>(tmA, tmB, tmO, tmO2, a, s);
-        case EPI_GELU: return launch_gemm_t<BN, EPI_GELU, STAGES>(tmA, tmB, tmO, tmO2, a, s);
-        case EPI_RESID: return launch_gemm_t<BN, EPI_RESID, STAGES>(tmA, tmB, tmO, tmO2, a, s);
-        case EPI_SWIGLU: return launch_gemm_t<BN, EPI_SWIGLU, STAGES>(tmA, tmB, tmO, tmO2, a, s);
-        case EPI_QKV_LLM: return launch_gemm_t<BN, EPI_QKV_LLM, STAGES>(tmA, tmB, tmO, tmO2, a, s);
-        case EPI_QKV_VIT: return launch_gemm_t<BN, EPI_QKV_VIT, STAGES>(tmA, tmB, tmO, tmO2, a, s);
-        case EPI_PATCH: return launch_gemm_t<BN, EPI_PATCH, STAGES>(tmA, tmB, tmO, tmO2, a, s);
-        case EPI_SCATTER: return launch_gemm_t<BN, EPI_SCATTER, STAGES>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_STORE: return launch_gemm_t<BN, EPI_STORE, STAGES, CG>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_GELU: return launch_gemm_t<BN, EPI_GELU, STAGES, CG>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_RESID: return launch_gemm_t<BN, EPI_RESID, STAGES, CG>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_SWIGLU: return launch_gemm_t<BN, EPI_SWIGLU, STAGES, CG>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_QKV_LLM: return launch_gemm_t<BN, EPI_QKV_LLM, STAGES, CG>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_QKV_VIT: return launch_gemm_t<BN, EPI_QKV_VIT, STAGES, CG>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_PATCH: return launch_gemm_t<BN, EPI_PATCH, STAGES, CG>(tmA, tmB, tmO, tmO2, a, s);
+        case EPI_SCATTER: return launch_gemm_t<BN, EPI_SCATTER, STAGES, CG>(tmA, tmB, tmO, tmO2, a, s);
         default: return set_error(MJV_ERR_ARG, "unknown GEMM epilogue %d", epi);
     }
 }
@@ -61,16 +81,26 @@ int gemm_bf16(const mjv_gemm_desc& d, cudaStream_t stream) {
     if (d.epilogue == EPI_PATCH) MJV_CHECK(d.pos_emb && d.seq > 0, MJV_ERR_ARG, "gemm: PATCH needs pos_emb/seq");
     if (d.epilogue == EPI_SCATTER) MJV_CHECK(d.row_map != nullptr, MJV_ERR_ARG, "gemm: SCATTER needs row_map");
 
+    // CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles) whenever the tile width allows it
+    int cg = d.cta_group;
+    if (cg == 0) {
+        static const int env_cg = getenv("MJV_GEMM_CG") ? atoi(getenv("MJV_GEMM_CG")) : 0;
+        // measured on B200: pairs win clearly up to K = 2048; at K >= 4096 the main loop dominates and single CTAs
+        // (4 x 48 KB stages) are on par or slightly ahead
+        cg = env_cg != 0 ? env_cg : (d.K >= 4096 ? 1 : 2);
+    }
+    if (bn != 256 || d.M <= 128) cg = 1;
+    MJV_CHECK(cg == 1 || cg == 2, MJV_ERR_ARG, "gemm: cta_group must be 1 or 2");
     CUtensorMap tmA, tmB;
     MJV_PROPAGATE(make_tmap_2d(&tmA, d.a, (uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.lda, 128));
-    MJV_PROPAGATE(make_tmap_2d(&tmB, d.w, (uint64_t)d.N, (uint64_t)d.K, (uint64_t)d.ldw, (uint32_t)bn));
+    MJV_PROPAGATE(make_tmap_2d(&tmB, d.w, (uint64_t)d.N, (uint64_t)d.K, (uint64_t)d.ldw, (uint32_t)(bn / cg)));
 
     GemmArgs a;
     memset(&a, 0, sizeof(a));
     a.M = d.M;
     a.N = d.N;
     a.K = d.K;
-    a.num_m_blocks = (d.M + 127) / 128;
+    a.num_m_blocks = (d.M + 128 * cg - 1) / (128 * cg);
     a.num_n_blocks = d.N / bn;
     a.out = static_cast<__nv_bfloat16*>(d.out);
     a.ldo = (int)d.ldo;
@@ -116,8 +146,9 @@ int gemm_bf16(const mjv_gemm_desc& d, cudaStream_t stream) {
             MJV_PROPAGATE(make_tmap_2d(&tmO2, d.residual, rows, cols, (uint64_t)d.ldr, 32));
         }
     }
-    if (bn == 256) return dispatch_epi<256, 4>(d.epilogue, tmA, tmB, tmO, tmO2, a, stream);
-    return dispatch_epi<128, 6>(d.epilogue, tmA, tmB, tmO, tmO2, a, stream);
+    if (bn == 256 && cg == 2) return dispatch_epi<256, 6, 2>(d.epilogue, tmA, tmB, tmO, tmO2, a, stream);
+    if (bn == 256) return dispatch_epi<256, 4, 1>(d.epilogue, tmA, tmB, tmO, tmO2, a, stream);
+    return dispatch_epi<128, 6, 1>(d.epilogue, tmA, tmB, tmO, tmO2, a, stream);
 }
 
 }  // namespace mjv

@@ -62,17 +62,30 @@ constexpr int BK = 64;
 constexpr int kThreads = 384;
 constexpr int kEpiWarps = 8;
 
-__device__ __forceinline__ float gelu_erf(float x) {
-    // 0.5*x*(1+erf(x/sqrt2)); erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution)
-    const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    p *= t;
-    const float e = 1.0f - p * __expf(-z * z);
-    return 0.5f * x * (1.0f + copysignf(e, x));
+// Exact-erf GELU on a pair of values with packed fp32x2 math and ONE MUFU per element (the chip is power-capped in
+// these GEMMs: every epilogue instruction costs main-loop clock).
+// erf by Abramowitz-Stegun 7.1.28: 1 - erf(z) = (1 + a1 z + ... + a6 z^6)^-16 =: r16, |err| <= 3e-7 (far below bf16
+// resolution). gelu(x) = 0.5 x (1 + erf(x/sqrt2)) = max(x, 0) - 0.5 |x| r16(|x|/sqrt2), which also keeps the relative
+// accuracy of the negative tail.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+    const uint64_t ax2 = ptx::pack_f32x2(fabsf(x0), fabsf(x1));
+    const uint64_t z2 = ptx::fmul2(ax2, ptx::pack_f32x2(0.70710678f, 0.70710678f));
+    uint64_t d2 = ptx::ffma2(ptx::pack_f32x2(0.0000430638f, 0.0000430638f), z2, ptx::pack_f32x2(0.0002765672f, 0.0002765672f));
+    d2 = ptx::ffma2(d2, z2, ptx::pack_f32x2(0.0001520143f, 0.0001520143f));
+    d2 = ptx::ffma2(d2, z2, ptx::pack_f32x2(0.0092705272f, 0.0092705272f));
+    d2 = ptx::ffma2(d2, z2, ptx::pack_f32x2(0.0422820123f, 0.0422820123f));
+    d2 = ptx::ffma2(d2, z2, ptx::pack_f32x2(0.0705230784f, 0.0705230784f));
+    d2 = ptx::ffma2(d2, z2, ptx::pack_f32x2(1.0f, 1.0f));
+    float d0, d1;
+    ptx::unpack_f32x2(d2, d0, d1);
+    uint64_t r2 = ptx::pack_f32x2(__fdividef(1.0f, d0), __fdividef(1.0f, d1));
+    r2 = ptx::fmul2(r2, r2);
+    r2 = ptx::fmul2(r2, r2);
+    r2 = ptx::fmul2(r2, r2);
+    r2 = ptx::fmul2(r2, r2);  // r^16 = 1 - erf(|z|)
+    const uint64_t h2 = ptx::fmul2(ax2, ptx::pack_f32x2(-0.5f, -0.5f));
+    const uint64_t o2 = ptx::ffma2(h2, r2, ptx::pack_f32x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+    ptx::unpack_f32x2(o2, x0, x1);
 }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
@@ -95,10 +108,10 @@ __device__ __forceinline__ void store32_bf16(__nv_bfloat16* p, const uint32_t* u
 
 constexpr int kStagingBytesPerWarp = 32 * 128;  // [32 rows][64 bf16] swizzled tile for one TMA store
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG = 1>
 struct SmemLayout {
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBBytes = (BN / CG) * BK * 2;  // cta_group::2: each CTA of the pair stages half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr bool kTmaStore = (BN == 256);  // 64-column output boxes per epilogue warp need BN/2 >= 128
     static constexpr int kStagingOffset = STAGES * kStageBytes;
@@ -108,13 +121,15 @@ struct SmemLayout {
 
 }  // namespace gemm_detail
 
-template <int BN, int EPI, int STAGES>
+// CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cluster of 2) per 256 x BN tile with tcgen05 cta_group::2 —
+// each CTA holds 128 rows of A, half of the B tile and the accumulator of its 128 rows; the leader CTA issues the MMAs.
+template <int BN, int EPI, int STAGES, int CG>
 __global__ void __launch_bounds__(gemm_detail::kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
                     const GemmArgs args) {
     using namespace gemm_detail;
-    using L = SmemLayout<BN, STAGES>;
+    using L = SmemLayout<BN, STAGES, CG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -128,8 +143,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = args.num_m_blocks * args.num_n_blocks;
+    const int num_tiles = args.num_m_blocks * args.num_n_blocks;  // tiles of (128*CG) x BN
     const int nkb = (args.K + BK - 1) / BK;
+    const int cta_rank = CG == 2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+    const int tile0 = blockIdx.x / CG;       // first tile of this CTA (pair)
+    const int tile_step = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
@@ -137,22 +155,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&full_bar[s], CG);  // one producer arrival per CTA of the pair (leader's barrier is used)
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
-            ptx::mbar_init(&tmem_empty[a], kEpiWarps);  // one arrive per epilogue warp
+            ptx::mbar_init(&tmem_empty[a], kEpiWarps * CG);  // one arrive per epilogue warp (of both CTAs)
         }
         for (int w = 0; w < kEpiWarps; ++w) ptx::mbar_init(&res_bar[w], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_slot, 2 * BN);
-        ptx::tmem_relinquish();
+        if constexpr (CG == 2) {
+            ptx::tmem_alloc_cg2(tmem_slot, 2 * BN);
+            ptx::tmem_relinquish_cg2();
+        } else {
+            ptx::tmem_alloc(tmem_slot, 2 * BN);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync();  // peer barriers are initialised before any remote arrive / TMA
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -161,11 +185,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / args.num_n_blocks) * BM;
-                const int n0 = (tile % args.num_n_blocks) * BN;
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+                const int m0 = (tile / args.num_n_blocks) * (BM * CG) + cta_rank * BM;
+                const int n0 = (tile % args.num_n_blocks) * BN + cta_rank * (BN / CG);
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if constexpr (CG == 2) {
+                        // both CTAs' bytes complete on the leader's barrier
+                        if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+                        else ptx::mbar_arrive_leader(&full_bar[stage]);
+                        ptx::tma_load_2d_cg2(sA + stage * L::kABytes, &tmA, &full_bar[stage], kb * BK, m0, ptx::kEvictNormal);
+                        ptx::tma_load_2d_cg2(sB + stage * L::kBBytes, &tmB, &full_bar[stage], kb * BK, n0, ptx::kEvictLast);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
                     ptx::tma_load_2d(sA + stage * L::kABytes, &tmA, &full_bar[stage], kb * BK, m0, ptx::kEvictNormal);
                     ptx::tma_load_2d(sB + stage * L::kBBytes, &tmB, &full_bar[stage], kb * BK, n0, ptx::kEvictLast);
@@ -176,15 +212,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer
+    } else if (warp == 1 && cta_rank == 0) {
+        // ===================================================== MMA issuer (leader CTA only when CG == 2)
         if (ptx::elect_one()) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * CG, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -195,11 +231,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint64_t bdesc = ptx::make_desc_sw128(ptx::smem_u32(sB + stage * L::kBBytes));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        ptx::mma_bf16_ss(d_tmem, ptx::desc_advance_k16(adesc, k), ptx::desc_advance_k16(bdesc, k),
-                                         idesc, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (CG == 2)
+                            ptx::mma_bf16_ss_cg2(d_tmem, ptx::desc_advance_k16(adesc, k), ptx::desc_advance_k16(bdesc, k),
+                                                 idesc, (kb | k) != 0 ? 1u : 0u);
+                        else
+                            ptx::mma_bf16_ss(d_tmem, ptx::desc_advance_k16(adesc, k), ptx::desc_advance_k16(bdesc, k),
+                                             idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::mma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-                    if (kb == nkb - 1) ptx::mma_commit(&tmem_full[acc]);
+                    if constexpr (CG == 2) {
+                        ptx::mma_commit_cg2(&empty_bar[stage]);  // frees the smem slot in BOTH CTAs
+                        if (kb == nkb - 1) ptx::mma_commit_cg2(&tmem_full[acc]);
+                    } else {
+                        ptx::mma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                        if (kb == nkb - 1) ptx::mma_commit(&tmem_full[acc]);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -242,8 +287,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t res_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / args.num_n_blocks) * BM;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            const int m0 = (tile / args.num_n_blocks) * (BM * CG) + cta_rank * BM;
             const int n0 = (tile % args.num_n_blocks) * BN;
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < args.M;
@@ -319,13 +364,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float x0 = ptx::bf16_round(__uint_as_float(v[2 * i]) + ptx::bf16_lo(b[i]));
-                        float x1 = ptx::bf16_round(__uint_as_float(v[2 * i + 1]) + ptx::bf16_hi(b[i]));
-                        if constexpr (EPI == EPI_GELU) {
-                            x0 = gelu_erf(x0);
-                            x1 = gelu_erf(x1);
-                        }
+                        float x0, x1;
+                        ptx::unpack_f32x2(ptx::fadd2(ptx::pack_f32x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
+                                                     ptx::pack_f32x2(ptx::bf16_lo(b[i]), ptx::bf16_hi(b[i]))),
+                                          x0, x1);
+                        // GELU is applied to the fp32 pre-activation (the reference rounds fc1's output to bf16 first;
+                        // the difference is below one bf16 ulp of the result). STORE/PATCH round once in the final pack.
+                        if constexpr (EPI == EPI_GELU) gelu_erf2(x0, x1);
                         if constexpr (EPI == EPI_RESID) {
+                            x0 = ptx::bf16_round(x0);
+                            x1 = ptx::bf16_round(x1);
                             if (args.scale != nullptr) {
                                 x0 = ptx::bf16_round(x0 * ptx::bf16_lo(s[i]));
                                 x1 = ptx::bf16_round(x1 * ptx::bf16_hi(s[i]));
@@ -334,8 +382,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             x1 += ptx::bf16_hi(r[i]);
                         }
                         if constexpr (EPI == EPI_PATCH) {
-                            x0 += ptx::bf16_lo(r[i]);
-                            x1 += ptx::bf16_hi(r[i]);
+                            x0 = ptx::bf16_round(x0) + ptx::bf16_lo(r[i]);
+                            x1 = ptx::bf16_round(x1) + ptx::bf16_hi(r[i]);
                         }
                         o[i] = ptx::pack_bf16x2(x0, x1);
                     }
@@ -509,7 +557,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if constexpr (CG == 2) ptx::mbar_arrive_leader(&tmem_empty[acc]);
+                else ptx::mbar_arrive(&tmem_empty[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -517,10 +568,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync();  // no CTA of the pair may exit while the other can still signal it
+    else __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, 2 * BN);
+        if constexpr (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, 2 * BN);
+        else ptx::tmem_dealloc(tmem_base, 2 * BN);
     }
 }
 

@@ -81,10 +81,14 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     // algorithmic FLOPs: 4*heads*hd*S^2 per sequence (bidirectional); causal work is supplied by the caller (flops_hint)
     double work = d.flops_hint;
     if (!varlen) work = 4.0 * d.heads * hd * (double)d.seq_len * d.seq_len * d.nseq;
-    dim3 grid;
-    if (varlen) grid = dim3((unsigned)d.n_work, (unsigned)d.heads, 1);
-    else grid = dim3((unsigned)((d.seq_len + 127) / 128), (unsigned)d.heads, (unsigned)d.nseq);
-
+    // persistent grid: 2 CTAs per SM (registers / smem / TMEM allow exactly two), static round-robin over the items
+    const int n_qblocks = varlen ? 0 : (d.seq_len + 127) / 128;
+    const long long n_items = varlen ? (long long)d.n_work * d.heads : (long long)d.nseq * d.heads * n_qblocks;
+    MJV_CHECK(n_items > 0 && n_items < (1LL << 31), MJV_ERR_ARG, "attention: bad item count %lld", n_items);
+    a.n_items = (int)n_items;
+    a.n_qblocks = n_qblocks;
+    const int max_ctas = 2 * sm_count();
+    dim3 grid((unsigned)(n_items < max_ctas ? n_items : max_ctas), 1, 1);
     if (hd == 64) {
         if (d.causal) return launch_attn_t<64, true>(tq, tk, tv, a, grid, stream, work);
         return launch_attn_t<64, false>(tq, tk, tv, a, grid, stream, work);

@@ -279,6 +279,8 @@ def run_mjv(args):
         lib.mjv_profile_enable(0)
         agg = {}
         for name, t_ms, work in _lib.profile_collect():
+            if name.startswith("gemm_"):
+                name = f"{name}[{work / 1e12:.2f}TF]"   # one line per GEMM shape
             a = agg.setdefault(name, dict(launches=0, ms=0.0, work=0.0))
             a["launches"] += 1
             a["ms"] += t_ms

@@ -214,6 +214,9 @@ typedef struct mjv_batch {
     const int32_t* work;       /* device [2*n_work] (sequence, 128-row query block), heavy first              */
     const int32_t* gather_rows;/* device [2B]: packed rows of the last real token (moe_reward.py:226-228) then
                                   of the gating token (find_token_for_gating, moe_reward.py:50-57)            */
+    const int32_t* work_last;  /* device [2*n_work_last]: the (sequence, query block) items that contain a gathered
+                                  row — the only attention blocks the LAST decoder layer needs (NULL = all)    */
+    int32_t n_work_last;
 } mjv_batch;
 
 typedef struct mjv_outputs {

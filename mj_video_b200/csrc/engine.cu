@@ -357,10 +357,12 @@ size_t proj_temp_bytes(const Dims& d, long long T) {
     const size_t Mp = static_cast<size_t>(T) * d.tok_per_tile;
     return al(Mp * 4 * d.C * 2) + al(Mp * d.D * 2) + 4096;
 }
-size_t llm_temp_bytes(const Dims& d, long long M, long long vt_cols) {
+size_t llm_temp_bytes(const Dims& d, long long M, long long vt_cols, long long B) {
     const size_t m = static_cast<size_t>(M);
+    const size_t g2 = static_cast<size_t>(2 * B);
     return al(m * d.D * 2) + al(m * d.Hq * d.hd * 2) + al(m * d.Hkv * d.hd * 2) +
-           al(static_cast<size_t>(d.Hkv) * d.hd * vt_cols * 2) + al(m * d.Hq * d.hd * 2) + al(m * d.F * 2) + 16384;
+           al(static_cast<size_t>(d.Hkv) * d.hd * vt_cols * 2) + al(m * d.Hq * d.hd * 2) + al(m * d.F * 2) +
+           al(g2 * d.Hq * d.hd * 2) + 2 * al(g2 * d.D * 2) + al(g2 * d.F * 2) + 16384;
 }
 size_t head_temp_bytes(const mjv_config& c, long long B) {
     return 4 * al(static_cast<size_t>(B) * c.gating_hidden * 2) + 3 * al(static_cast<size_t>(B) * 32 * 2) + 8192;
@@ -521,8 +523,17 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
     // alignment-pad columns of V^T are never written: keep them finite (they are multiplied by exact zeros)
     MJV_CUDA_OK(cudaMemsetAsync(vt, 0, vt_bytes, st));
 
+    // compact buffers of the last layer: only the 2 rows per sample the head reads go through wo / MLP / final norm
+    const int G2 = 2 * b.n_rows;
+    const bool shortcut = b.work_last != nullptr && b.n_work_last > 0;
+    MJV_ALLOC(att_c, __nv_bfloat16*, ar, static_cast<size_t>(G2) * nq * 2);
+    MJV_ALLOC(h_c, __nv_bfloat16*, ar, static_cast<size_t>(G2) * d.D * 2);
+    MJV_ALLOC(xn_c, __nv_bfloat16*, ar, static_cast<size_t>(G2) * d.D * 2);
+    MJV_ALLOC(mid_c, __nv_bfloat16*, ar, static_cast<size_t>(G2) * d.F * 2);
+
     for (int i = 0; i < c.llm_layers; ++i) {
         const LlmLayerW& w = h->llm[i];
+        const bool last = shortcut && (i == c.llm_layers - 1);
         MJV_PROPAGATE(rmsnorm(hcur, w.attn_norm, xn, M, d.D, c.rms_eps, nullptr, st));
         {
             mjv_gemm_desc g = gemm_base(xn, d.D, w.wqkv, d.D, q, nq, (int)M, nq + 2 * nk, d.D, MJV_EPI_QKV_LLM);
@@ -557,34 +568,53 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
             a.causal = 1;
             a.nseq = b.n_rows;
             a.cu_seqlens = b.cu_seqlens;
-            a.work = b.work;
-            a.n_work = b.n_work;
+            // the last layer only needs the query blocks that hold a gathered row (its K/V still cover every token)
+            a.work = last ? b.work_last : b.work;
+            a.n_work = last ? b.n_work_last : b.n_work;
             a.vt_starts = b.vt_starts;
             a.vt_cols = b.vt_cols;
-            a.flops_hint = b.attn_flops;
+            a.flops_hint = last ? 0.0 : b.attn_flops;
             a.scale = 1.0f / sqrtf(static_cast<float>(d.hd));
             MJV_PROPAGATE(attention(a, st));
         }
+        __nv_bfloat16* hres = hcur;   // residual stream of the rows processed from here on
+        const __nv_bfloat16* att_in = att;
+        __nv_bfloat16* xn_in = xn;
+        __nv_bfloat16* mid_in = mid;
+        int rows = (int)M;
+        if (last) {
+            MJV_PROPAGATE(gather_rows(att, b.gather_rows, att_c, G2, nq, st));
+            MJV_PROPAGATE(gather_rows(hcur, b.gather_rows, h_c, G2, d.D, st));
+            hres = h_c;
+            att_in = att_c;
+            xn_in = xn_c;
+            mid_in = mid_c;
+            rows = G2;
+        }
         {
-            mjv_gemm_desc g = gemm_base(att, nq, w.wo, nq, hcur, d.D, (int)M, d.D, nq, MJV_EPI_RESID);
-            g.residual = hcur;
+            mjv_gemm_desc g = gemm_base(att_in, nq, w.wo, nq, hres, d.D, rows, d.D, nq, MJV_EPI_RESID);
+            g.residual = hres;
             g.ldr = d.D;
             MJV_PROPAGATE(gemm_bf16(g, st));
         }
-        MJV_PROPAGATE(rmsnorm(hcur, w.ffn_norm, xn, M, d.D, c.rms_eps, nullptr, st));
+        MJV_PROPAGATE(rmsnorm(hres, w.ffn_norm, xn_in, rows, d.D, c.rms_eps, nullptr, st));
         {
-            mjv_gemm_desc g = gemm_base(xn, d.D, w.w13, d.D, mid, d.F, (int)M, 2 * d.F, d.D, MJV_EPI_SWIGLU);
+            mjv_gemm_desc g = gemm_base(xn_in, d.D, w.w13, d.D, mid_in, d.F, rows, 2 * d.F, d.D, MJV_EPI_SWIGLU);
             MJV_PROPAGATE(gemm_bf16(g, st));
         }
         {
-            mjv_gemm_desc g = gemm_base(mid, d.F, w.w2, d.F, hcur, d.D, (int)M, d.D, d.F, MJV_EPI_RESID);
-            g.residual = hcur;
+            mjv_gemm_desc g = gemm_base(mid_in, d.F, w.w2, d.F, hres, d.D, rows, d.D, d.F, MJV_EPI_RESID);
+            g.residual = hres;
             g.ldr = d.D;
             MJV_PROPAGATE(gemm_bf16(g, st));
         }
     }
     // final norm only on the 2 rows per sample the head reads (hidden_states[-1][b, idx]: moe_reward.py:211,236-243)
-    MJV_PROPAGATE(rmsnorm(hcur, h->final_norm, gathered, 2LL * b.n_rows, d.D, c.rms_eps, b.gather_rows, st));
+    if (shortcut) {
+        MJV_PROPAGATE(rmsnorm(h_c, h->final_norm, gathered, G2, d.D, c.rms_eps, nullptr, st));
+    } else {
+        MJV_PROPAGATE(rmsnorm(hcur, h->final_norm, gathered, G2, d.D, c.rms_eps, b.gather_rows, st));
+    }
     return 0;
 }
 
@@ -722,7 +752,7 @@ extern "C" int64_t mjv_workspace_bytes(const mjv_handle* h, int32_t n_rows, int3
     size_t temp = vit_temp_bytes(d, n_tiles);
     size_t t2 = proj_temp_bytes(d, n_tiles);
     if (t2 > temp) temp = t2;
-    t2 = llm_temp_bytes(d, n_tokens, vt_cols);
+    t2 = llm_temp_bytes(d, n_tokens, vt_cols, n_rows);
     if (t2 > temp) temp = t2;
     t2 = head_temp_bytes(h->cfg, n_rows);
     if (t2 > temp) temp = t2;

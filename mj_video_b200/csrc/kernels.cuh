@@ -15,6 +15,7 @@ int rmsnorm(const void* x, const void* w, void* out, long long rows, int C, floa
             cudaStream_t st);
 int embed_tokens(const int* ids, const void* table, void* out, long long rows, int C, int img_ctx_id, int vocab,
                  cudaStream_t st);
+int gather_rows(const void* src, const int* idx, void* dst, int rows, int C, cudaStream_t st);
 int im2col_patches(const void* px, int px_dtype, void* out, int T, int img, int ps, int Kpad, cudaStream_t st);
 int cls_rows(const void* cls, const void* pos, void* hidden, int T, int S, int C, cudaStream_t st);
 int preprocess_frames(const void* frames, int F, int H, int W, int image_size, int max_num, int use_thumbnail,

@@ -149,31 +149,51 @@ embed_kernel(const int* __restrict__ ids, const __nv_bfloat16* __restrict__ tabl
     for (int c = lane; c < C / 8; c += 32) dst[c] = __ldg(src + c);
 }
 
+// dst[i,:] = src[idx[i],:] (bf16 rows, C multiple of 8)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ idx, __nv_bfloat16* __restrict__ dst,
+                   int rows, int C) {
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<long long>(idx[row]) * C);
+    uint4* d = reinterpret_cast<uint4*>(dst + static_cast<long long>(row) * C);
+    for (int c = lane; c < C / 8; c += 32) d[c] = s[c];
+}
+
 // ------------------------------------------------------------------------------------------------ patch im2col
 // pixel_values [T,3,H,W] (bf16 or fp32) -> A[T*P, Kpad] bf16 with k = c*ps*ps + ky*ps + kx (the flattening of
 // nn.Conv2d's weight, modeling_intern_vit.py:164), zero padded to Kpad so rows are 16-byte aligned for TMA.
 template <typename TIn>
-__global__ void im2col_kernel(const TIn* __restrict__ px, __nv_bfloat16* __restrict__ out, int T, int img, int ps,
-                              int Kpad) {
+__global__ void __launch_bounds__(256)
+im2col_kernel(const TIn* __restrict__ px, __nv_bfloat16* __restrict__ out, int T, int img, int ps, int Kpad) {
+    // one thread = 8 consecutive k of one patch row of A (one 16-byte store); 32-bit index arithmetic throughout
     const int g = img / ps;
-    const long long total = static_cast<long long>(T) * g * g * Kpad;
     const int K = 3 * ps * ps;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int k = static_cast<int>(i % Kpad);
-        const long long p = i / Kpad;
-        float val = 0.f;
-        if (k < K) {
-            const int c = k / (ps * ps);
-            const int rem = k - c * ps * ps;
-            const int ky = rem / ps, kx = rem - ky * ps;
-            const int pj = static_cast<int>(p % g);
-            const long long tp = p / g;
-            const int pi = static_cast<int>(tp % g);
-            const long long t = tp / g;
-            val = static_cast<float>(px[((t * 3 + c) * img + (pi * ps + ky)) * img + (pj * ps + kx)]);
+    const int kvec = Kpad / 8;
+    const unsigned total = static_cast<unsigned>(T) * g * g * kvec;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned p = i / kvec;          // patch index over all tiles
+        const int k0 = (i - p * kvec) * 8;
+        const unsigned tp = p / g;
+        const int pj = p - tp * g;
+        const unsigned t = tp / g;
+        const int pi = tp - t * g;
+        const TIn* base = px + (static_cast<size_t>(t) * 3 * img + pi * ps) * img + pj * ps;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = k0 + e;
+            float val = 0.f;
+            if (k < K) {
+                const int c = k / (ps * ps);
+                const int rem = k - c * ps * ps;
+                const int ky = rem / ps, kx = rem - ky * ps;
+                val = static_cast<float>(base[(static_cast<size_t>(c) * img + ky) * img + kx]);
+            }
+            f[e] = val;
         }
-        out[i] = __float2bfloat16_rn(val);
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(p) * Kpad + k0) = pack8(f);
     }
 }
 
@@ -242,6 +262,18 @@ int rmsnorm(const void* x, const void* w, void* out, long long rows, int C, floa
     else if (nchunk <= 8) MJV_RMS(8);
     else MJV_RMS(16);
 #undef MJV_RMS
+    MJV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int gather_rows(const void* src, const int* idx, void* dst, int rows, int C, cudaStream_t st) {
+    if (rows == 0) return 0;
+    MJV_CHECK(C % 8 == 0, MJV_ERR_ARG, "gather_rows: C=%d", C);
+    {
+        LaunchScope scope(TAG_EMBED, st, 4.0 * rows * C);
+        gather_rows_kernel<<<(rows + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(
+            (const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, rows, C);
+    }
     MJV_CUDA_OK(cudaGetLastError());
     return 0;
 }

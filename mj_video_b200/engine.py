@@ -215,10 +215,15 @@ class Engine:
         work.sort(key=lambda t: -t[1])
         work = np.asarray(work, dtype=np.int32).reshape(-1, 2)
         gather = np.concatenate([cu[:-1] + last, cu[:-1] + gate]).astype(np.int32)
+        # the last decoder layer only needs the attention blocks that contain a gathered row
+        work_last = sorted({(s, int(last[s]) // 128) for s in range(B)} | {(s, int(gate[s]) // 128) for s in range(B)},
+                           key=lambda t: -t[1])
+        work_last = np.asarray(work_last, dtype=np.int32).reshape(-1, 2)
         meta = dict(token_ids=token_ids, row_pos=row_pos, row_vt=row_vt, img_rows=img_rows,
                     cu_seqlens=cu.astype(np.int32), vt_starts=vt_starts.astype(np.int32), work=work.reshape(-1),
-                    gather_rows=gather)
+                    gather_rows=gather, work_last=work_last.reshape(-1))
         return meta, dict(B=B, M=M, vt_cols=int(vt_cols), n_work=int(work.shape[0]), n_img=int(img_rows.size),
+                          n_work_last=int(work_last.shape[0]),
                           lengths=lengths, last=last, gate=gate)
 
     def upload_meta(self, meta: dict) -> tuple[torch.Tensor, dict]:
@@ -276,8 +281,10 @@ class Engine:
             hd = d.llm_hidden // d.llm_heads
             b.attn_flops = float(sum(4.0 * d.llm_heads * hd * n * (n + 1) / 2 for n in info["lengths"].tolist()))
             b.pixel_values, b.pixel_dtype = px.data_ptr(), _DTYPES[px.dtype]
-            for k in ("token_ids", "row_pos", "row_vt", "img_rows", "cu_seqlens", "vt_starts", "work", "gather_rows"):
+            for k in ("token_ids", "row_pos", "row_vt", "img_rows", "cu_seqlens", "vt_starts", "work", "gather_rows",
+                      "work_last"):
                 setattr(b, k, base + 4 * off[k])
+            b.n_work_last = info["n_work_last"]
             o = _lib.Outputs()
             o.scores, o.extras = sb.scores.data_ptr(), sb.extras.data_ptr()
             o.hidden_state, o.prompt_embedding = sb.hidden.data_ptr(), sb.prompt.data_ptr()

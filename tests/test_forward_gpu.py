@@ -221,3 +221,23 @@ def test_full_size_2b_row_vs_oracle(gpu):
     # same caption, two different videos -> the decision matches the oracle's
     s, r = mine["score"].float().cpu(), o32["score"].float().cpu()
     assert (s[0] > s[1]) == (r[0] > r[1]) or abs(r[0] - r[1]) < 5e-3
+
+
+def test_long_visual_sequence_config4_shapes(tiny_engine, gpu):
+    """BASELINE configs[3] shapes on the small model: 16 frames of 896x1344 -> dynamic_preprocess max_num=6 -> 7 tiles per
+    frame = 112 tiles, N = 28 8xx tokens in ONE row (resize kernels, 226 query blocks, RoPE positions up to ~29k)."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from oracle import port
+    d, sd, eng = tiny_engine
+    vid = synth.make_video(77, n_frames=32, height=896, width=1344)
+    pv, counts = load_video(vid, num_segments=16, max_num=6, device="cuda", dtype=torch.bfloat16)
+    assert counts == [7] * 16 and pv.shape[0] == 112
+    ref_pv, ref_counts = port.load_video_frames(vid[:4], num_segments=2, max_num=6)   # spot-check the resize path
+    got_pv, _ = load_video(vid[:4], num_segments=2, max_num=6)
+    assert ref_counts == [7, 7] and torch.equal(got_pv, ref_pv)
+    ids, mask = synth.pad_batch([synth.make_input_ids(3, counts, n_cap=46)])
+    assert ids.shape[1] == 48 + 16 * (5 + 256 * 7) + 46 + 5 == 28851
+    mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
+    ref = port.Oracle(d, sd, dtype=torch.float32, device=gpu).forward(pv.float(), ids, mask)
+    _check(mine, ref)

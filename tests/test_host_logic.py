@@ -52,6 +52,10 @@ def test_prepare_batch_indices_match_reference_semantics():
     work = meta["work"].reshape(-1, 2)
     assert sorted(map(tuple, work.tolist())) == sorted((s, q) for s in range(3) for q in range((len(rows[s]) + 127) // 128))
     assert (np.diff(work[:, 1]) <= 0).all()
+    # last-layer shortcut: exactly the query blocks that hold a gathered row
+    wl = set(map(tuple, meta["work_last"].reshape(-1, 2).tolist()))
+    exp = {(b, (len(rows[b]) - 1) // 128) for b in range(3)} | {(b, port.find_token_for_gating(rows[b]) // 128) for b in range(3)}
+    assert wl == exp and info["n_work_last"] == len(exp)
 
 
 def test_prepare_batch_errors():

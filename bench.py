@@ -24,6 +24,33 @@ sys.path.insert(0, ROOT)
 METRIC = "video pairs scored/sec @8x448^2 frames"
 UNIT = "pairs/s"
 WORKLOAD = "MJ-VIDEO-2B bf16, batch of 32 synthetic text-video pairs per GPU, 8 frames 448^2, max_num=1 (BASELINE configs[1])"
+# other BASELINE configs, selectable for measurement (the default line is configs[1]):
+WORKLOADS = {
+    ("2b", "pairs8"): WORKLOAD,
+    ("2b", "long16x7"): "MJ-VIDEO-2B bf16, long-visual-sequence rows: 16 frames 896x1344, dynamic_preprocess max_num=6 -> "
+                        "7 tiles per frame, 112 tiles and ~28.9k tokens per row (BASELINE configs[3])",
+    ("4b", "pairs8"): "InternViT-300M + Phi-3-mini-shaped LLM (d 3072, 32 layers, 32 heads x 96; reference Llama branch), "
+                      "full 28-criterion MoE head, bf16, 32 synthetic pairs per GPU, 8 frames 448^2 (BASELINE configs[4])",
+    ("4b", "long16x7"): "config-5 model on config-4 rows",
+}
+
+
+def model_dims(name):
+    from mj_video_b200 import synth
+    return synth.dims_2b() if name == "2b" else synth.dims_4b()
+
+
+def step_flops(d, n_tiles, lengths):
+    """Algorithmic FLOPs of one step: ViT + projector per tile, LLM linear + causal-exact attention per
+    row; LM head, padding and the non-causal half of attention excluded."""
+    C, S, P, Fv, Lv = d.vit_hidden, d.vit_seq, d.patches_per_tile, d.vit_mlp, d.vit_layers
+    k_patch = 3 * d.patch_size ** 2
+    f_tile = 2 * P * k_patch * C + Lv * (2 * S * C * 3 * C + 2 * S * C * C + 4 * S * C * Fv + 4 * S * S * C)
+    D, F, L, H, KV, hd = d.llm_hidden, d.llm_inter, d.llm_layers, d.llm_heads, d.llm_kv_heads, d.llm_head_dim
+    tpt = d.tokens_per_tile
+    f_proj = 2 * tpt * 4 * C * D + 2 * tpt * D * D
+    f_tok = L * 2 * (D * (H + 2 * KV) * hd + H * hd * D + 3 * D * F)
+    return n_tiles * (f_tile + f_proj) + sum(n * f_tok + L * 4 * H * hd * n * (n + 1) / 2 for n in lengths)
 
 
 def peaks():
@@ -71,17 +98,21 @@ class ClockSampler(threading.Thread):
                     samples=len(s))
 
 
-def make_rows(n_rows: int, first_row: int, n_frames: int = 8):
-    """Synthetic workload rows: row r = video id r, caption ids seeded by the PAIR (chosen/rejected share a caption)."""
+def make_rows(n_rows: int, first_row: int, n_frames: int = 8, workload: str = "pairs8"):
+    """Synthetic workload rows: row r = video id r, caption ids seeded by the PAIR (chosen/rejected share a caption).
+    long16x7: 32-frame 896x1344 videos, 16 sampled frames, 7 tiles per frame."""
     import numpy as np
     from mj_video_b200 import synth
     from mj_video_b200.data_processor import get_index
     frames, rows = [], []
+    long_ = workload == "long16x7"
+    if long_:
+        n_frames = 16
     for r in range(first_row, first_row + n_rows):
-        vid = synth.make_video(r, n_frames=16)
+        vid = synth.make_video(r, n_frames=32, height=896, width=1344) if long_ else synth.make_video(r, n_frames=16)
         idx = get_index(None, 8.0, len(vid) - 1, 0, n_frames)
         frames.append(vid[idx])
-        rows.append(synth.make_input_ids(r // 2, [1] * n_frames))
+        rows.append(synth.make_input_ids(r // 2, [7 if long_ else 1] * n_frames, n_cap=46 if long_ else None))
     return np.concatenate(frames), rows
 
 
@@ -163,24 +194,27 @@ def run_mjv(args):
     lib = _lib.load()
     pk = peaks()
 
-    d = synth.dims_2b()
+    d = model_dims(args.model)
     sd = synth.make_state_dict(d, seed=1234, include_lm_head=False)
     eng = Engine(EngineDims.from_synth(d), dev)
     eng.load_state_dict(sd)
+    del sd
+    workload = WORKLOADS[(args.model, args.workload)]
+    max_num = 6 if args.workload == "long16x7" else 1
 
     B = args.batch
-    frames_np, rows = make_rows(B, rank * B)                      # rank r scores pairs [r*B/2, (r+1)*B/2)
+    frames_np, rows = make_rows(B, rank * B, workload=args.workload)   # rank r scores pairs [r*B/2, (r+1)*B/2)
     ids, mask = synth.pad_batch(rows)
     frames_host = torch.from_numpy(frames_np).pin_memory()
     frames_dev = frames_host.to(dev)
-    T = frames_dev.shape[0]
+    T = frames_dev.shape[0] * (7 if max_num == 6 else 1)
     px = torch.empty((T, 3, 448, 448), dtype=torch.bfloat16, device=dev)
     sb = eng.stage_batch(px, ids, mask, synth.PAD, synth.IMG_CONTEXT)
     n_pairs_total = world * B // 2
     lengths = sb.info["lengths"].tolist()
 
     def step_resident():
-        preprocess_frames(frames_dev, 448, 1, True, torch.bfloat16, out=px)
+        preprocess_frames(frames_dev, 448, max_num, True, torch.bfloat16, out=px)
         out = eng.run(sb)
         if world > 1:
             return allgather_scores(out["scores"], n_pairs_total)
@@ -235,10 +269,7 @@ def run_mjv(args):
                     launches_timed=len(k_ms), avg_launch_ms=avg_ms, flops_per_launch=k_flops)
 
     # whole-step algorithmic FLOPs -> end-to-end fraction of the tensor roofline
-    F_tile = 2 * 1024 * 588 * 1024 + 24 * (2 * 1025 * 1024 * 3072 + 2 * 1025 * 1024 ** 2 + 4 * 1025 * 1024 * 4096 +
-                                           4 * 1025 ** 2 * 1024)
-    F_proj = 2 * 256 * 4096 * 2048 + 2 * 256 * 2048 ** 2
-    F_step = T * (F_tile + F_proj) + sum(n * 3.0199e9 + 24 * 4096 * n * (n + 1) for n in lengths)
+    F_step = step_flops(d, T, lengths)
     step_tflops = F_step * args.steps / (ms * 1e-3) / 1e12
 
     # ---------------------------------------------------------------- end to end through the public API (`e2e`)
@@ -249,7 +280,7 @@ def run_mjv(args):
 
     def step_e2e():
         fdev = frames_host.to(dev, non_blocking=True)              # H2D of this step's uint8 frames (pinned)
-        pv, _ = pf(fdev, 448, 1, True, torch.bfloat16)
+        pv, _ = pf(fdev, 448, max_num, True, torch.bfloat16)
         out = eng.forward(pv, ids_cpu, mask_cpu, synth.PAD, synth.IMG_CONTEXT)  # host indexing + meta H2D + kernels
         scores = out["scores"]
         if world > 1:
@@ -297,9 +328,9 @@ def run_mjv(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sd_full = dict(sd)
-        sd_full["model.language_model.output.weight"] = torch.zeros((d.vocab, d.llm_hidden))
-        secs = cpu_forward_seconds(d, sd_full, cores)
+        d2 = synth.dims_2b()
+        sd_full = synth.make_state_dict(d2, seed=1234, include_lm_head=True)
+        secs = cpu_forward_seconds(d2, sd_full, cores)
         cpu_baseline = dict(value=1.0 / secs, unit=UNIT, cores=cores, kind="port",
                             sample=f"1 row (BASELINE configs[0]: 8 frames 448^2, fp32, eager attention, incl. the "
                                    f"reference's unused LM-head matmul), one forward = {secs:.1f} s on {cores} threads")
@@ -308,7 +339,7 @@ def run_mjv(args):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                     data="synthetic",
-                    config=dict(workload=WORKLOAD, rows_per_gpu=B, tiles_per_gpu=T, tokens_per_gpu=M_tokens,
+                    config=dict(workload=workload, rows_per_gpu=B, tiles_per_gpu=T, tokens_per_gpu=M_tokens,
                                 l2="inputs and activations per step (0.15 GB uint8 frames, >5 GB activations) exceed the 126 MB L2",
                                 parallelism=f"dp{world} over preference pairs (chosen/rejected on one rank) + 1 all-gather"),
                     e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
@@ -325,10 +356,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mjv", choices=["mjv", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="rows (text-video pairs) per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="rows (text-video pairs) per GPU per step (default 32; 2 for long16x7)")
+    ap.add_argument("--model", default="2b", choices=["2b", "4b"], help="2b = MJ-VIDEO-2B (BASELINE configs[0-3]); 4b = configs[4] shapes")
+    ap.add_argument("--workload", default="pairs8", choices=["pairs8", "long16x7"], help="pairs8 = configs[1]; long16x7 = configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write a per-kernel time breakdown JSON here (rank 0)")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 2 if args.workload == "long16x7" else 32
     args.warmup = max(args.warmup, 3) if args.impl == "mjv" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -24,6 +24,7 @@ struct Tensor {
     long long rows = 0, cols = 0, ld = 0;
     bool is_float = false;
     long long filled_rows = 0;
+    long long expect_rows = -1;  // source rows that make the tensor complete (-1: all of `rows`)
 };
 
 struct VitLayerW {
@@ -83,7 +84,7 @@ struct Arena {
 // ------------------------------------------------------------------------------------------------ weight ingestion
 __global__ void convert_rows_kernel(const void* __restrict__ src, int src_dtype, long long rows, long long cols,
                                     __nv_bfloat16* __restrict__ dst, long long dst_ld,
-                                    const int* __restrict__ dst_row_map) {
+                                    const int* __restrict__ dst_row_map, const int* __restrict__ dst_col_map) {
     const long long total = rows * cols;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -93,11 +94,20 @@ __global__ void convert_rows_kernel(const void* __restrict__ src, int src_dtype,
         else if (src_dtype == MJV_DTYPE_BF16) v = __bfloat162float(static_cast<const __nv_bfloat16*>(src)[i]);
         else v = __half2float(static_cast<const __half*>(src)[i]);
         const long long dr = dst_row_map != nullptr ? dst_row_map[r] : r;
-        dst[dr * dst_ld + c] = __float2bfloat16_rn(v);
+        const long long dc = dst_col_map != nullptr ? dst_col_map[c] : c;
+        dst[dr * dst_ld + dc] = __float2bfloat16_rn(v);
     }
 }
 
 size_t dtype_size(int dt) { return dt == MJV_DTYPE_F32 ? 4 : 2; }
+
+// LLM heads narrower than 128 (e.g. 96 for the Phi-3-mini-shaped backbone of BASELINE configs[4]) are stored in a
+// 128-wide slot so that the head_dim-128 RoPE epilogue and attention kernel serve them unchanged: the two rotary
+// halves go to columns [0, hd/2) and [64, 64 + hd/2) (rotate-half pairs column c with c + 64), V keeps its order, and
+// every pad column comes from an all-zero weight row, i.e. is exactly 0 in q, k, v and the attention output. The
+// permutation is applied to q and k alike, so q.k is unchanged; `wo` gets matching zero columns.
+constexpr int kHeadSlot = 128;
+inline int qk_slot_dim(int d, int hd) { return d < hd / 2 ? d : 64 + (d - hd / 2); }
 
 bool ends_with(const std::string& s, const char* suf) {
     const size_t n = strlen(suf);
@@ -175,9 +185,10 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
     }
 
     const int hd = c.llm_hidden / c.llm_heads;
+    const int hs = kHeadSlot;
     std::string dst_key = key;
     long long dst_rows = rows, dst_ld = cols;
-    std::vector<int> row_map;
+    std::vector<int> row_map, col_map;
     if (ends_with(key, "patch_embedding.weight")) {
         dst_ld = h->kpad;
     } else if (ends_with(key, "attention.wqkv.weight")) {
@@ -185,25 +196,38 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
         const int g = c.llm_heads / c.llm_kv_heads;
         MJV_CHECK(rows == static_cast<long long>(c.llm_heads + 2 * c.llm_kv_heads) * hd, MJV_ERR_ARG,
                   "%s: unexpected rows %lld", key.c_str(), rows);
+        dst_rows = static_cast<long long>(c.llm_heads + 2 * c.llm_kv_heads) * hs;
         row_map.resize(rows);
         for (int kv = 0; kv < c.llm_kv_heads; ++kv)
             for (int s = 0; s < g + 2; ++s)
                 for (int d = 0; d < hd; ++d) {
                     const int src = (kv * (g + 2) + s) * hd + d;
                     int dst;
-                    if (s < g) dst = (kv * g + s) * hd + d;
-                    else if (s == g) dst = c.llm_heads * hd + kv * hd + d;
-                    else dst = (c.llm_heads + c.llm_kv_heads) * hd + kv * hd + d;
+                    if (s < g) dst = (kv * g + s) * hs + qk_slot_dim(d, hd);
+                    else if (s == g) dst = (c.llm_heads + kv) * hs + qk_slot_dim(d, hd);
+                    else dst = (c.llm_heads + c.llm_kv_heads + kv) * hs + d;
                     row_map[src] = dst;
                 }
     } else if (ends_with(key, "attention.wq.weight") || ends_with(key, "attention.wk.weight") ||
                ends_with(key, "attention.wv.weight")) {
         const char which = key[key.size() - 8];  // 'q' / 'k' / 'v'
         dst_key = key.substr(0, key.size() - 9) + "wqkv.weight";
-        dst_rows = static_cast<long long>(c.llm_heads + 2 * c.llm_kv_heads) * hd;
-        const int base = which == 'q' ? 0 : (which == 'k' ? c.llm_heads * hd : (c.llm_heads + c.llm_kv_heads) * hd);
+        dst_rows = static_cast<long long>(c.llm_heads + 2 * c.llm_kv_heads) * hs;
+        const int n_heads = which == 'q' ? c.llm_heads : c.llm_kv_heads;
+        MJV_CHECK(rows == static_cast<long long>(n_heads) * hd, MJV_ERR_ARG, "%s: unexpected rows %lld", key.c_str(), rows);
+        const int base = which == 'q' ? 0 : (which == 'k' ? c.llm_heads : c.llm_heads + c.llm_kv_heads);
         row_map.resize(rows);
-        for (long long r = 0; r < rows; ++r) row_map[r] = base + static_cast<int>(r);
+        for (long long r = 0; r < rows; ++r) {
+            const int head = static_cast<int>(r / hd), d = static_cast<int>(r % hd);
+            row_map[r] = (base + head) * hs + (which == 'v' ? d : qk_slot_dim(d, hd));
+        }
+    } else if (ends_with(key, "attention.wo.weight")) {
+        MJV_CHECK(cols == static_cast<long long>(c.llm_heads) * hd, MJV_ERR_ARG, "%s: unexpected cols %lld", key.c_str(), cols);
+        dst_ld = static_cast<long long>(c.llm_heads) * hs;
+        if (hd != hs) {
+            col_map.resize(cols);
+            for (long long cc = 0; cc < cols; ++cc) col_map[cc] = static_cast<int>((cc / hd) * hs + cc % hd);
+        }
     } else if (ends_with(key, "feed_forward.w1.weight") || ends_with(key, "feed_forward.w3.weight")) {
         // gate/up interleaved in 32-row chunks so one GEMM tile holds both halves of SwiGLU
         const bool is_up = key[key.size() - 8] == '3';
@@ -216,22 +240,29 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
 
     Tensor* t;
     MJV_PROPAGATE(ensure_tensor(h, dst_key, dst_rows, cols, dst_ld, false, &t));
+    if (ends_with(dst_key, "attention.wqkv.weight"))
+        t->expect_rows = static_cast<long long>(c.llm_heads + 2 * c.llm_kv_heads) * hd;
     void* staging = nullptr;
     MJV_CUDA_OK(cudaMalloc(&staging, n_elem * dtype_size(dtype)));
-    int* map_dev = nullptr;
+    int *map_dev = nullptr, *cmap_dev = nullptr;
     cudaError_t e = cudaMemcpy(staging, data, n_elem * dtype_size(dtype), cudaMemcpyDefault);
     if (e == cudaSuccess && !row_map.empty()) {
         e = cudaMalloc(&map_dev, row_map.size() * sizeof(int));
         if (e == cudaSuccess) e = cudaMemcpy(map_dev, row_map.data(), row_map.size() * sizeof(int), cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess && !col_map.empty()) {
+        e = cudaMalloc(&cmap_dev, col_map.size() * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpy(cmap_dev, col_map.data(), col_map.size() * sizeof(int), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) {
         convert_rows_kernel<<<sm_count() * 4, 256>>>(staging, dtype, rows, cols, static_cast<__nv_bfloat16*>(t->ptr),
-                                                     t->ld, map_dev);
+                                                     t->ld, map_dev, cmap_dev);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaDeviceSynchronize();  // load time only; the compute path never synchronises
     }
     cudaFree(staging);
     if (map_dev) cudaFree(map_dev);
+    if (cmap_dev) cudaFree(cmap_dev);
     if (e != cudaSuccess) return set_error(MJV_ERR_CUDA, "mjv_load_weight(%s): %s", key_c, cudaGetErrorString(e));
     t->filled_rows += rows;
     return 0;
@@ -240,9 +271,10 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
 int need(mjv_handle* h, const std::string& key, const void** out, long long rows = -1) {
     auto it = h->weights.find(key);
     if (it == h->weights.end()) return set_error(MJV_ERR_STATE, "missing weight: %s", key.c_str());
-    if (it->second.filled_rows < it->second.rows)
+    const long long want = it->second.expect_rows >= 0 ? it->second.expect_rows : it->second.rows;
+    if (it->second.filled_rows < want)
         return set_error(MJV_ERR_STATE, "weight %s only partially loaded (%lld of %lld rows)", key.c_str(),
-                         it->second.filled_rows, it->second.rows);
+                         it->second.filled_rows, want);
     if (rows >= 0 && it->second.rows * it->second.cols != rows)
         return set_error(MJV_ERR_STATE, "weight %s has %lld elements, expected %lld", key.c_str(),
                          it->second.rows * it->second.cols, rows);
@@ -297,10 +329,10 @@ int finalize(mjv_handle* h) {
     }
     MJV_PROPAGATE(need(h, lm + "norm.weight", &h->final_norm));
     const void* tmp;
-    const int hd = c.llm_hidden / c.llm_heads;
-    MJV_PROPAGATE(need(h, "rope.cos", &tmp, static_cast<long long>(c.max_pos) * (hd / 2)));
+    // [max_pos, 64]: one column per rotary pair of the 128-wide head slot (pad pairs: cos 1, sin 0)
+    MJV_PROPAGATE(need(h, "rope.cos", &tmp, static_cast<long long>(c.max_pos) * (kHeadSlot / 2)));
     h->rope_cos = static_cast<const float*>(tmp);
-    MJV_PROPAGATE(need(h, "rope.sin", &tmp, static_cast<long long>(c.max_pos) * (hd / 2)));
+    MJV_PROPAGATE(need(h, "rope.sin", &tmp, static_cast<long long>(c.max_pos) * (kHeadSlot / 2)));
     h->rope_sin = static_cast<const float*>(tmp);
     MJV_PROPAGATE(need(h, "regression_layer.weight", &h->regression));
     MJV_PROPAGATE(need(h, "reward_transform_matrix", &h->transform));
@@ -322,7 +354,7 @@ int finalize(mjv_handle* h) {
 // ------------------------------------------------------------------------------------------------ sizes
 struct Dims {
     int S, P, C, Fv, heads, Kpad, Spad, tok_per_tile;
-    int D, F, Hq, Hkv, hd;
+    int D, F, Hq, Hkv, hd, hs;  // hd: model head_dim; hs: stored head slot (128)
 };
 Dims dims_of(const mjv_handle* h) {
     const mjv_config& c = h->cfg;
@@ -341,6 +373,7 @@ Dims dims_of(const mjv_handle* h) {
     d.Hq = c.llm_heads;
     d.Hkv = c.llm_kv_heads;
     d.hd = c.llm_hidden / c.llm_heads;
+    d.hs = kHeadSlot;
     return d;
 }
 inline size_t al(size_t bytes) { return (bytes + 1023) & ~size_t(1023); }
@@ -360,9 +393,9 @@ size_t proj_temp_bytes(const Dims& d, long long T) {
 size_t llm_temp_bytes(const Dims& d, long long M, long long vt_cols, long long B) {
     const size_t m = static_cast<size_t>(M);
     const size_t g2 = static_cast<size_t>(2 * B);
-    return al(m * d.D * 2) + al(m * d.Hq * d.hd * 2) + al(m * d.Hkv * d.hd * 2) +
-           al(static_cast<size_t>(d.Hkv) * d.hd * vt_cols * 2) + al(m * d.Hq * d.hd * 2) + al(m * d.F * 2) +
-           al(g2 * d.Hq * d.hd * 2) + 2 * al(g2 * d.D * 2) + al(g2 * d.F * 2) + 16384;
+    return al(m * d.D * 2) + al(m * d.Hq * d.hs * 2) + al(m * d.Hkv * d.hs * 2) +
+           al(static_cast<size_t>(d.Hkv) * d.hs * vt_cols * 2) + al(m * d.Hq * d.hs * 2) + al(m * d.F * 2) +
+           al(g2 * d.Hq * d.hs * 2) + 2 * al(g2 * d.D * 2) + al(g2 * d.F * 2) + 16384;
 }
 size_t head_temp_bytes(const mjv_config& c, long long B) {
     return 4 * al(static_cast<size_t>(B) * c.gating_hidden * 2) + 3 * al(static_cast<size_t>(B) * 32 * 2) + 8192;
@@ -508,15 +541,15 @@ int project_and_splice(mjv_handle* h, const void* vit_hidden, const mjv_batch& b
 int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered, Arena& ar, cudaStream_t st) {
     const Dims d = dims_of(h);
     const mjv_config& c = h->cfg;
-    MJV_CHECK(d.hd == 128, MJV_ERR_ARG, "LLM head_dim %d unsupported (128 only)", d.hd);
+    MJV_CHECK(d.hd % 2 == 0 && d.hd >= 2 && d.hd <= d.hs, MJV_ERR_ARG, "LLM head_dim %d unsupported (even, <= 128)", d.hd);
     const long long M = b.n_tokens;
     MJV_CHECK(M > 0 && M < (1LL << 31) / 16, MJV_ERR_ARG, "bad token count %lld", M);
-    const int nq = d.Hq * d.hd, nk = d.Hkv * d.hd;
+    const int nq = d.Hq * d.hs, nk = d.Hkv * d.hs;
     __nv_bfloat16* hcur = static_cast<__nv_bfloat16*>(embeds);
     MJV_ALLOC(xn, __nv_bfloat16*, ar, static_cast<size_t>(M) * d.D * 2);
     MJV_ALLOC(q, __nv_bfloat16*, ar, static_cast<size_t>(M) * nq * 2);
     MJV_ALLOC(k, __nv_bfloat16*, ar, static_cast<size_t>(M) * nk * 2);
-    const size_t vt_bytes = static_cast<size_t>(d.Hkv) * d.hd * b.vt_cols * 2;
+    const size_t vt_bytes = static_cast<size_t>(d.Hkv) * d.hs * b.vt_cols * 2;
     MJV_ALLOC(vt, __nv_bfloat16*, ar, vt_bytes);
     MJV_ALLOC(att, __nv_bfloat16*, ar, static_cast<size_t>(M) * nq * 2);
     MJV_ALLOC(mid, __nv_bfloat16*, ar, static_cast<size_t>(M) * d.F * 2);
@@ -545,7 +578,7 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
             g.row_vt = b.row_vt;
             g.n_q_cols = nq;
             g.n_k_cols = nk;
-            g.vt_stride_head = static_cast<long long>(d.hd) * b.vt_cols;
+            g.vt_stride_head = static_cast<long long>(d.hs) * b.vt_cols;
             g.vt_ld = static_cast<int>(b.vt_cols);
             MJV_PROPAGATE(gemm_bf16(g, st));
         }
@@ -560,9 +593,9 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
             a.ldk = nk;
             a.ldo = nq;
             a.vt_ld = b.vt_cols;
-            a.vt_plane_stride = static_cast<long long>(d.hd) * b.vt_cols;
+            a.vt_plane_stride = static_cast<long long>(d.hs) * b.vt_cols;
             a.total_rows = M;
-            a.head_dim = d.hd;
+            a.head_dim = d.hs;
             a.heads = d.Hq;
             a.kv_heads = d.Hkv;
             a.causal = 1;

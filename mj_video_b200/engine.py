@@ -71,7 +71,8 @@ class EngineDims:
         """From mj_video_b200.synth.ModelDims."""
         return EngineDims(
             image_size=d.image_size, patch_size=d.patch_size, vit_hidden=d.vit_hidden, vit_heads=d.vit_heads,
-            vit_mlp=d.vit_mlp, vit_layers=d.vit_layers, vit_eps=d.vit_eps, llm_arch=0, llm_hidden=d.llm_hidden,
+            vit_mlp=d.vit_mlp, vit_layers=d.vit_layers, vit_eps=d.vit_eps,
+            llm_arch=1 if getattr(d, "llm_arch", "") == "LlamaForCausalLM" else 0, llm_hidden=d.llm_hidden,
             llm_inter=d.llm_inter, llm_layers=d.llm_layers, llm_heads=d.llm_heads, llm_kv_heads=d.llm_kv_heads,
             vocab=d.vocab, rms_eps=d.rms_eps, rope_theta=d.rope_theta, max_pos=d.max_pos,
             num_objectives=d.num_objectives, num_aspects=d.num_aspects, gating_hidden=d.gating_hidden,
@@ -93,9 +94,10 @@ _DTYPES = {torch.float32: _lib.MJV_DTYPE_F32, torch.bfloat16: _lib.MJV_DTYPE_BF1
 class Engine:
     """One model on one CUDA device. Not thread-safe (like the reference nn.Module)."""
 
-    def __init__(self, dims: EngineDims, device: torch.device | str = "cuda"):
+    def __init__(self, dims: EngineDims, device: torch.device | str = "cuda", rope_inv_freq_bf16: bool = True):
         self.lib = _lib.load()
         self.dims = dims
+        self.rope_inv_freq_bf16 = rope_inv_freq_bf16
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.MjvError("mj_video_b200 runs on CUDA devices only (no CPU fallback)")
@@ -132,15 +134,25 @@ class Engine:
 
     # -------------------------------------------------------------------------------------------- weights
     def _load_rope(self):
-        """cos/sin tables exactly as InternLM2RotaryEmbedding builds them (modeling_internlm2.py:147-170): fp32 on the
-        host; in bf16 models the buffers are cast with the model, so the table holds bf16-rounded values."""
+        """cos/sin tables as the reference's rotary modules produce them in a bf16 model, one column per rotary pair of
+        the 128-wide head slot the kernels use (pairs beyond head_dim/2 are padding: cos 1, sin 0).
+        InternLM2 (modeling_internlm2.py:147-170): fp32 tables built at init, cast with the model -> bf16-rounded values.
+        Llama branch (modeling_internvl_chat.py:125-126 -> transformers LlamaRotaryEmbedding): `inv_freq` is a buffer,
+        so `model.to(bfloat16)` rounds inv_freq itself to bf16; angles are then computed in fp32 and cos/sin cast to
+        bf16. `rope_inv_freq_bf16=False` keeps fp32 inv_freq (a bf16 checkpoint loaded without a later `.to()`)."""
         d = self.dims
         hd = d.llm_hidden // d.llm_heads
+        if hd % 2 or hd > 128:
+            raise _lib.MjvError(f"LLM head_dim {hd} unsupported (even, <= 128)")
         inv_freq = 1.0 / (d.rope_theta ** (torch.arange(0, hd, 2).float() / hd))
+        if d.llm_arch == 1 and self.rope_inv_freq_bf16:
+            inv_freq = inv_freq.to(torch.bfloat16).float()
         t = torch.arange(d.max_pos, dtype=inv_freq.dtype)
         freqs = torch.einsum("i,j->ij", t, inv_freq)
-        cos = freqs.cos().to(torch.bfloat16).to(torch.float32).contiguous()
-        sin = freqs.sin().to(torch.bfloat16).to(torch.float32).contiguous()
+        cos = torch.ones((d.max_pos, 64), dtype=torch.float32)
+        sin = torch.zeros((d.max_pos, 64), dtype=torch.float32)
+        cos[:, : hd // 2] = freqs.cos().to(torch.bfloat16).to(torch.float32)
+        sin[:, : hd // 2] = freqs.sin().to(torch.bfloat16).to(torch.float32)
         self.load_weight("rope.cos", cos)
         self.load_weight("rope.sin", sin)
 

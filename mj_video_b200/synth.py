@@ -37,7 +37,9 @@ class ModelDims:
     vit_layers: int = 24
     vit_eps: float = 1e-6
     vit_ls_init: float = 0.1
-    # LLM (InternLM2)
+    # LLM (InternLM2, or the HF-Llama branch of modeling_internvl_chat.py:125-126)
+    llm_arch: str = "InternLM2ForCausalLM"
+    template: str = "internlm2-chat"
     llm_hidden: int = 2048
     llm_inter: int = 8192
     llm_layers: int = 24
@@ -81,6 +83,21 @@ class ModelDims:
 def dims_2b() -> ModelDims:
     """MJ-VIDEO-2B = InternVL2-2B (InternViT-300M + InternLM2-1.8B) + MoE head (BASELINE.json configs 1-4)."""
     return ModelDims()
+
+
+def dims_4b() -> ModelDims:
+    """BASELINE.json configs[4]: InternViT-300M + a Phi-3-mini-*shaped* LLM run through the reference's Llama branch
+    (SURVEY §A.1, §8(a) A12): d 3072, 32 layers, 32 heads x 96, MHA, plain RoPE theta 1e4. The vocabulary stays at
+    92 553 because moe_reward.py:45-48 hard-codes InternLM2 token ids for the gating pattern."""
+    return ModelDims(name="mjvideo-4b-shaped", llm_arch="LlamaForCausalLM", template="phi3-chat", llm_hidden=3072,
+                     llm_inter=8192, llm_layers=32, llm_heads=32, llm_kv_heads=32, rope_theta=10000.0)
+
+
+def dims_tiny_llama() -> ModelDims:
+    """Small Llama-branch model with head_dim 96 (the config-5 head shape) and grouped KV heads."""
+    return ModelDims(name="tiny-llama", llm_arch="LlamaForCausalLM", template="phi3-chat", vit_hidden=128, vit_heads=2,
+                     vit_mlp=256, vit_layers=2, llm_hidden=384, llm_inter=512, llm_layers=2, llm_heads=4,
+                     llm_kv_heads=2, gating_hidden=128, rope_theta=10000.0)
 
 
 def dims_tiny() -> ModelDims:
@@ -134,19 +151,30 @@ def make_state_dict(d: ModelDims, seed: int = 1234, include_lm_head: bool = True
     lm = "model.language_model."
     D = d.llm_hidden
     hd = d.llm_head_dim
-    sd[lm + "model.tok_embeddings.weight"] = 0.02 * torch.randn((d.vocab, D), generator=g)
+    llama = d.llm_arch == "LlamaForCausalLM"
+    # key names of the two LLM branches (modeling_internlm2.py vs transformers LlamaForCausalLM)
+    names = dict(emb="model.embed_tokens", wo="self_attn.o_proj", w1="mlp.gate_proj", w3="mlp.up_proj",
+                 w2="mlp.down_proj", n1="input_layernorm", n2="post_attention_layernorm", head="lm_head") if llama else \
+        dict(emb="model.tok_embeddings", wo="attention.wo", w1="feed_forward.w1", w3="feed_forward.w3",
+             w2="feed_forward.w2", n1="attention_norm", n2="ffn_norm", head="output")
+    sd[lm + names["emb"] + ".weight"] = 0.02 * torch.randn((d.vocab, D), generator=g)
     for i in range(d.llm_layers):
         p = f"{lm}model.layers.{i}."
-        sd[p + "attention.wqkv.weight"] = 0.02 * torch.randn(((d.llm_heads + 2 * d.llm_kv_heads) * hd, D), generator=g)
-        sd[p + "attention.wo.weight"] = 0.02 * torch.randn((D, d.llm_heads * hd), generator=g)
-        sd[p + "feed_forward.w1.weight"] = 0.02 * torch.randn((d.llm_inter, D), generator=g)
-        sd[p + "feed_forward.w3.weight"] = 0.02 * torch.randn((d.llm_inter, D), generator=g)
-        sd[p + "feed_forward.w2.weight"] = 0.02 * torch.randn((D, d.llm_inter), generator=g)
-        _norm(sd, g, p + "attention_norm", D, bias=False)
-        _norm(sd, g, p + "ffn_norm", D, bias=False)
+        if llama:
+            sd[p + "self_attn.q_proj.weight"] = 0.02 * torch.randn((d.llm_heads * hd, D), generator=g)
+            sd[p + "self_attn.k_proj.weight"] = 0.02 * torch.randn((d.llm_kv_heads * hd, D), generator=g)
+            sd[p + "self_attn.v_proj.weight"] = 0.02 * torch.randn((d.llm_kv_heads * hd, D), generator=g)
+        else:
+            sd[p + "attention.wqkv.weight"] = 0.02 * torch.randn(((d.llm_heads + 2 * d.llm_kv_heads) * hd, D), generator=g)
+        sd[p + names["wo"] + ".weight"] = 0.02 * torch.randn((D, d.llm_heads * hd), generator=g)
+        sd[p + names["w1"] + ".weight"] = 0.02 * torch.randn((d.llm_inter, D), generator=g)
+        sd[p + names["w3"] + ".weight"] = 0.02 * torch.randn((d.llm_inter, D), generator=g)
+        sd[p + names["w2"] + ".weight"] = 0.02 * torch.randn((D, d.llm_inter), generator=g)
+        _norm(sd, g, p + names["n1"], D, bias=False)
+        _norm(sd, g, p + names["n2"], D, bias=False)
     _norm(sd, g, lm + "model.norm", D, bias=False)
     if include_lm_head:
-        sd[lm + "output.weight"] = 0.02 * torch.randn((d.vocab, D), generator=g)
+        sd[lm + names["head"] + ".weight"] = 0.02 * torch.randn((d.vocab, D), generator=g)
     c4 = C * int(1 / d.downsample_ratio) ** 2
     _norm(sd, g, "model.mlp1.0", c4)
     _linear(sd, g, "model.mlp1.1", D, c4)

@@ -69,6 +69,17 @@ def main():
     fix["outputs_row0_alone"] = {k: v.float().clone() for k, v in out1.items()}
     torch.save(fix, os.path.join(GOLD, "tiny_forward.pt"))
 
+    # ---------------- Llama branch (modeling_internvl_chat.py:125-126), head_dim 96 (BASELINE configs[4] head shape):
+    # fp32 forward and the reference's own bf16 forward (whose `.to(bfloat16)` also rounds the rotary inv_freq buffer)
+    dl = synth.dims_tiny_llama()
+    sdl = synth.make_state_dict(dl, seed=seed)
+    fixl = dict(dims="tiny-llama", seed=seed, video_ids=video_ids, n_caps=n_caps, pixel_sha256=sha(pv))
+    for name, dt in (("outputs", torch.float32), ("outputs_bf16", torch.bfloat16)):
+        ml = rh.build_reference_model(dl, sdl, dtype=dt)
+        o = rh.reference_forward(ml, pv.to(dt), ids, mask)
+        fixl[name] = {k: v.float().clone() for k, v in o.items()}
+    torch.save(fixl, os.path.join(GOLD, "tiny_llama_forward.pt"))
+
     # ---------------- frame-path goldens: checksums + a few probes of the reference's load_video output
     frames = {}
     for name, (H, W, mx, nseg) in {"448x448_m1": (448, 448, 1, 8), "896x1344_m6": (896, 1344, 6, 2),

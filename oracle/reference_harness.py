@@ -80,13 +80,15 @@ def build_reference_config(d):
                   num_hidden_layers=d.vit_layers, image_size=d.image_size, patch_size=d.patch_size,
                   qkv_bias=True, qk_normalization=False, norm_type="layer_norm", layer_norm_eps=d.vit_eps,
                   hidden_act="gelu", drop_path_rate=0.0, initializer_factor=d.vit_ls_init, use_flash_attn=False)
-    llm = dict(architectures=["InternLM2ForCausalLM"], hidden_size=d.llm_hidden, intermediate_size=d.llm_inter,
+    arch = getattr(d, "llm_arch", "InternLM2ForCausalLM")
+    llm = dict(architectures=[arch], hidden_size=d.llm_hidden, intermediate_size=d.llm_inter,
                num_hidden_layers=d.llm_layers, num_attention_heads=d.llm_heads, num_key_value_heads=d.llm_kv_heads,
-               vocab_size=d.vocab, rms_norm_eps=d.rms_eps, hidden_act="silu", bias=False, rope_theta=d.rope_theta,
-               max_position_embeddings=d.max_pos, rope_scaling={"type": "dynamic", "factor": 2.0},
-               attn_implementation="eager", use_cache=True, pad_token_id=2)
+               vocab_size=d.vocab, rms_norm_eps=d.rms_eps, hidden_act="silu", rope_theta=d.rope_theta,
+               max_position_embeddings=d.max_pos, attn_implementation="eager", use_cache=True, pad_token_id=2)
+    if arch == "InternLM2ForCausalLM":
+        llm.update(bias=False, rope_scaling={"type": "dynamic", "factor": 2.0})
     cfg = moe_reward.InternVLChatRewardModelingConfig(
-        vision_config=vision, llm_config=llm, template="internlm2-chat", downsample_ratio=d.downsample_ratio,
+        vision_config=vision, llm_config=llm, template=getattr(d, "template", "internlm2-chat"), downsample_ratio=d.downsample_ratio,
         ps_version="v2", select_layer=-1, force_image_size=d.image_size, num_objectives=d.num_objectives,
         num_aspects=d.num_aspects, aspect2criteria={k: list(v) for k, v in d.aspect2criteria.items()},
         gating_temperature=d.gating_temperature, gating_hidden_dim=d.gating_hidden, gating_n_hidden=d.gating_n_hidden)

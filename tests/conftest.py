@@ -30,6 +30,12 @@ def golden_forward():
 
 
 @pytest.fixture(scope="session")
+def golden_llama_forward():
+    import torch
+    return torch.load(os.path.join(GOLD, "tiny_llama_forward.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
 def golden_frames():
     with open(os.path.join(GOLD, "frames.json")) as f:
         return json.load(f)

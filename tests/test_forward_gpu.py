@@ -241,3 +241,69 @@ def test_long_visual_sequence_config4_shapes(tiny_engine, gpu):
     mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
     ref = port.Oracle(d, sd, dtype=torch.float32, device=gpu).forward(pv.float(), ids, mask)
     _check(mine, ref)
+
+
+def _llama_cfg(d):
+    from mj_video_b200.model import InternVLChatRewardModelingConfig
+    vision = dict(hidden_size=d.vit_hidden, num_attention_heads=d.vit_heads, intermediate_size=d.vit_mlp,
+                  num_hidden_layers=d.vit_layers, image_size=448, patch_size=14, qkv_bias=True, qk_normalization=False,
+                  norm_type="layer_norm", layer_norm_eps=d.vit_eps)
+    llm = dict(architectures=["LlamaForCausalLM"], hidden_size=d.llm_hidden, intermediate_size=d.llm_inter,
+               num_hidden_layers=d.llm_layers, num_attention_heads=d.llm_heads, num_key_value_heads=d.llm_kv_heads,
+               vocab_size=d.vocab, rms_norm_eps=d.rms_eps, rope_theta=d.rope_theta, max_position_embeddings=d.max_pos)
+    return InternVLChatRewardModelingConfig(
+        vision_config=vision, llm_config=llm, template="phi3-chat", downsample_ratio=0.5, ps_version="v2",
+        select_layer=-1, force_image_size=448, num_objectives=28, num_aspects=5, aspect2criteria=d.aspect2criteria,
+        gating_temperature=1.0, gating_hidden_dim=d.gating_hidden, gating_n_hidden=3)
+
+
+def test_llama_branch_head_dim_96_vs_reference_golden(gpu, golden_llama_forward):
+    """the Llama LLM branch (HF key names, separate q/k/v, head_dim 96 in a 128-wide slot, GQA)
+    through the drop-in module, against the real reference's fp32 AND bf16 forwards on the same seeds."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from mj_video_b200.model import InternVLChatRewardModeling
+    from oracle import port
+    fix = golden_llama_forward
+    d = synth.dims_tiny_llama()
+    sd = synth.make_state_dict(d, seed=fix["seed"])
+    m = InternVLChatRewardModeling("unused", _llama_cfg(d))
+    m.load_state_dict(sd, strict=True)
+    m.config.pad_token_id = synth.PAD
+    m = m.to(torch.bfloat16).cuda().eval()
+    m.model.img_context_token_id = synth.IMG_CONTEXT
+    pv = torch.cat([load_video(synth.make_video(v), num_segments=8, max_num=1)[0] for v in fix["video_ids"]])
+    rows = [synth.make_input_ids(i, [1] * 8, n_cap=n) for i, n in enumerate(fix["n_caps"])]
+    ids, mask = synth.pad_batch(rows)
+    out = m.forward(pv.to(torch.bfloat16).cuda(), ids.cuda(), mask.cuda())
+    _check(out, fix["outputs"])
+    _check(out, fix["outputs_bf16"])
+    # tighter, on the gathered hidden state, against the fp32 oracle using the bf16 model's (rounded) rotary inv_freq
+    o32 = port.Oracle(d, sd, dtype=torch.float32, device=gpu, inv_freq_dtype=torch.bfloat16).forward(
+        pv.cuda(), ids, mask)
+    o16 = port.Oracle(d, sd, dtype=torch.bfloat16, device=gpu).forward(pv.to(torch.bfloat16).cuda(), ids, mask)
+    drift = (o16["hidden_state"].float() - o32["hidden_state"]).abs().max().item()
+    assert (out.hidden_state.float() - o32["hidden_state"]).abs().max().item() <= 2 * drift + 1e-2
+    _check(out, o32)
+
+
+def test_config5_widths_vs_oracle(gpu):
+    """BASELINE configs[4] LLM widths (d 3072, 32 heads x 96, MHA, inter 8192, theta 1e4) with the layer counts cut to
+    keep the oracle fast: 2 rows x 8 frames against the oracle in bf16 and fp32."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from mj_video_b200.engine import Engine, EngineDims
+    from oracle import port
+    d = synth.dims_4b()
+    d.vit_layers, d.llm_layers = 2, 4
+    sd = synth.make_state_dict(d, seed=77, include_lm_head=False)
+    eng = Engine(EngineDims.from_synth(d), gpu)
+    eng.load_state_dict(sd)
+    pv = torch.cat([load_video(synth.make_video(300 + i), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)[0]
+                    for i in range(2)])
+    ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=30), synth.make_input_ids(1, [1] * 8, n_cap=71)])
+    mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
+    o16 = port.Oracle(d, sd, dtype=torch.bfloat16, device=gpu).forward(pv, ids, mask)
+    _check(mine, o16)
+    o32 = port.Oracle(d, sd, dtype=torch.float32, device=gpu, inv_freq_dtype=torch.bfloat16).forward(pv.float(), ids, mask)
+    _check(mine, o32)

@@ -38,6 +38,21 @@ def test_forward_matches_reference_golden(golden_forward):
         assert torch.allclose(out1[k].float(), ref, atol=2e-6, rtol=1e-5), k
 
 
+def test_llama_branch_matches_reference_golden(golden_llama_forward):
+    """Llama-branch LLM (modeling_internvl_chat.py:125-126) with head_dim 96, fp32 and the reference's bf16 forward."""
+    fix = golden_llama_forward
+    d = synth.dims_tiny_llama()
+    sd = synth.make_state_dict(d, seed=fix["seed"])
+    pv, ids, mask, _ = _inputs(fix)
+    out = port.Oracle(d, sd).forward(pv, ids, mask)
+    for k, ref in fix["outputs"].items():
+        assert torch.allclose(out[k].float(), ref, atol=2e-6, rtol=1e-5), (k, (out[k].float() - ref).abs().max())
+    out = port.Oracle(d, sd, dtype=torch.bfloat16).forward(pv.to(torch.bfloat16), ids, mask)
+    for k in ("rewards", "aspect_scores", "score", "aspect_gating_output"):
+        # bf16 CPU matmul kernels may differ between machines in summation order: a few bf16 ulp
+        assert torch.allclose(out[k].float(), fix["outputs_bf16"][k], atol=2e-2), k
+
+
 def test_output_contract(golden_forward):
     """Shapes/dtypes of CustomOutput as the reference returns them."""
     o = golden_forward["outputs"]

@@ -28,6 +28,22 @@ def test_forward_bit_exact_fp32(ref_model):
         assert torch.equal(ref[k].float(), out[k].float()), k
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_llama_branch_bit_exact(dtype):
+    """The reference's Llama LLM branch (modeling_internvl_chat.py:125-126, transformers LlamaForCausalLM) with
+    head_dim 96 and grouped KV heads; in bf16 the reference rounds the rotary inv_freq buffer too."""
+    from oracle import reference_harness as rh
+    d = synth.dims_tiny_llama()
+    sd = synth.make_state_dict(d, seed=5)
+    m = rh.build_reference_model(d, sd, dtype=dtype)
+    pv = torch.cat([rh.reference_load_video(synth.make_video(v), num_segments=8, max_num=1)[0] for v in (3, 4)]).to(dtype)
+    ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=46), synth.make_input_ids(1, [1] * 8, n_cap=20)])
+    ref = rh.reference_forward(m, pv, ids, mask)
+    out = port.Oracle(d, sd, dtype=dtype).forward(pv, ids, mask)
+    for k in ref:
+        assert torch.equal(ref[k].float(), out[k].float()), k
+
+
 def test_first_slot_layout(ref_model):
     """All IMG_CONTEXT tokens in the first <image> slot (what the reference's own callers produce)."""
     d, sd, m, rh = ref_model

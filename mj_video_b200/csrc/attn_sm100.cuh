@@ -387,14 +387,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         ptx::unpack_f32x2(ptx::fadd2(ps2[2], ps2[3]), s2, s3);
                         l_run += (s0 + s1) + (s2 + s3);
                     } else {
+                        // columns at or beyond wlim are invisible to every row of this warp (block tail / above the causal
+                        // diagonal): the branch is warp-uniform, so those pairs cost no exponentials
+                        const int wlim = CAUSAL ? min(valid, q0 + qw * 32 + 32 - kv0) : valid;
                         float psum = 0.0f;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i]), args.scale_log2, -m_run));
-                            float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), args.scale_log2, -m_run));
-                            p0 = (2 * i < lim) ? p0 : 0.0f;
-                            p1 = (2 * i + 1 < lim) ? p1 : 0.0f;
-                            psum += p0 + p1;
+                            float p0 = 0.0f, p1 = 0.0f;
+                            if (2 * i < wlim) {
+                                p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i]), args.scale_log2, -m_run));
+                                p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), args.scale_log2, -m_run));
+                                p0 = (2 * i < lim) ? p0 : 0.0f;
+                                p1 = (2 * i + 1 < lim) ? p1 : 0.0f;
+                                psum += p0 + p1;
+                            }
                             v[i] = ptx::pack_bf16x2(p0, p1);
                         }
                         l_run += psum;

@@ -307,3 +307,26 @@ def test_config5_widths_vs_oracle(gpu):
     _check(mine, o16)
     o32 = port.Oracle(d, sd, dtype=torch.float32, device=gpu, inv_freq_dtype=torch.bfloat16).forward(pv.float(), ids, mask)
     _check(mine, o32)
+
+
+def test_pair_scorer_matches_direct_forward(tiny_engine, gpu):
+    """BASELINE configs[2] driver (pipeline.PairScorer: collation thread, pinned H2D on a copy stream, frame kernels,
+    micro-batches, score table) against scoring the same rows with direct Engine.forward calls."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import preprocess_frames
+    from mj_video_b200.dist import preference_decisions
+    from mj_video_b200.pipeline import PairScorer, SyntheticPairs
+    d, sd, eng = tiny_engine
+    data = SyntheticPairs(5, first_video=900)
+    out = PairScorer.for_engine(eng, synth.PAD, synth.IMG_CONTEXT, rows_per_step=4).score(data)
+    assert out["scores"].shape == (10, 34) and out["rows_local"] == 10
+    ref = []
+    for k in range(5):
+        rows = data[k]
+        pv = torch.cat([preprocess_frames(torch.from_numpy(f).cuda(), 448, 1, True, torch.bfloat16)[0] for f, _ in rows])
+        ids, mask = synth.pad_batch([ids for _, ids in rows])
+        ref.append(eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT)["scores"].float().clone())
+    ref = torch.cat(ref)
+    # micro-batch composition differs (4 rows vs 2 rows per launch) but rows are independent: tiny bf16-level differences
+    assert (out["scores"] - ref).abs().max().item() < 1e-2
+    assert torch.equal(out["prefer"].cpu(), preference_decisions(out["scores"][:, -1]).cpu())

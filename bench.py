@@ -180,7 +180,7 @@ def run_mjv(args):
     import torch.distributed as dist
     from mj_video_b200 import _lib, synth
     from mj_video_b200.data_processor import preprocess_frames
-    from mj_video_b200.dist import allgather_scores
+    from mj_video_b200.dist import NcclScoreGather, allgather_scores
     from mj_video_b200.engine import Engine, EngineDims
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -213,12 +213,20 @@ def run_mjv(args):
     n_pairs_total = world * B // 2
     lengths = sb.info["lengths"].tolist()
 
+    # the data-path collective goes through the library's own C ABI (mjv_allgather_scores -> ncclAllGather over NVLink)
+    gather = NcclScoreGather(dev) if world > 1 else None
+
     def step_resident():
         preprocess_frames(frames_dev, 448, max_num, True, torch.bfloat16, out=px)
         out = eng.run(sb)
         if world > 1:
-            return allgather_scores(out["scores"], n_pairs_total)
+            return gather.gather(out["scores"], n_pairs_total)
         return out["scores"]
+
+    if world > 1:  # the C-ABI collective agrees with torch.distributed's on the same table
+        chk = eng.run(sb)["scores"]
+        if not torch.equal(gather.gather(chk, n_pairs_total), allgather_scores(chk, n_pairs_total)):
+            raise RuntimeError("mjv_allgather_scores disagrees with torch.distributed.all_gather_into_tensor")
 
     def barrier():
         if world > 1:
@@ -284,7 +292,7 @@ def run_mjv(args):
         out = eng.forward(pv, ids_cpu, mask_cpu, synth.PAD, synth.IMG_CONTEXT)  # host indexing + meta H2D + kernels
         scores = out["scores"]
         if world > 1:
-            scores = allgather_scores(scores, n_pairs_total)
+            scores = gather.gather(scores, n_pairs_total)
         return scores.cpu()                                       # D2H read of the result (synchronises)
 
     for _ in range(max(1, args.warmup // 2)):

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=64)
     ap.add_argument("--rows-per-step", type=int, default=32)
     ap.add_argument("--model", default="2b", choices=["2b", "4b", "tiny"])
+    ap.add_argument("--pool", type=int, default=64, help="distinct synthetic clips generated up front (0: one per row, host-bound)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -42,8 +43,10 @@ def main():
     eng = Engine(EngineDims.from_synth(d), dev)
     eng.load_state_dict(synth.make_state_dict(d, seed=1234, include_lm_head=False))
     scorer = PairScorer.for_engine(eng, synth.PAD, synth.IMG_CONTEXT, rows_per_step=args.rows_per_step)
-    data = SyntheticPairs(args.pairs)
-    scorer.score(SyntheticPairs(min(args.pairs, world * args.rows_per_step // 2)))   # warm-up
+    data = SyntheticPairs(args.pairs, pool=args.pool)
+    warm = SyntheticPairs(min(args.pairs, world * args.rows_per_step // 2))
+    warm.pool = data.pool
+    scorer.score(warm)   # warm-up
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

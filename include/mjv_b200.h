@@ -241,6 +241,21 @@ int mjv_score_forward(mjv_handle* h, const mjv_batch* batch, const mjv_outputs* 
                       int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: the ONE collective of the path. The reference issues no collective at all (its process group of
+ * size 1 exists only for torch.distributed.get_rank(): modeling_internvl_chat.py:172, eval_genai_mjvideo.py:24); sharding
+ * preference pairs over ranks adds an equal-count all-gather of the fp32 score table [rows_per_rank, width]
+ * (width = num_objectives + num_aspects + 1; a rank with fewer rows pads). NCCL is resolved at run time (dlopen).
+ *   mjv_comm_unique_id : rank 0 fills a 128-byte id which the caller distributes (torch.distributed store, MPI, ...)
+ *   mjv_comm_create    : every rank, with its CUDA device current; returns an opaque communicator (an ncclComm_t)
+ *   mjv_allgather_scores: enqueued on `stream`; out = [world * rows_per_rank, width], rank-major
+ * A caller that already owns an ncclComm_t may pass it to mjv_allgather_scores directly.
+ * ---------------------------------------------------------------------------------------------------------- */
+int mjv_comm_unique_id(void* id_128_bytes);
+int mjv_comm_create(const void* id_128_bytes, int32_t rank, int32_t world, void** comm_out);
+int mjv_comm_destroy(void* comm);
+int mjv_allgather_scores(void* comm, const float* local_rows, int64_t rows_per_rank, int32_t width, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Launch accounting and per-launch timing (used by bench.py; see csrc/launch.cuh for the tag list).
  * mjv_profile_enable(mask): bracket every launch whose tag bit is set with two CUDA events on the launching stream.
  * mjv_profile_read: elapsed ms + algorithmic work (FLOPs or bytes) per recorded launch; clears the records.

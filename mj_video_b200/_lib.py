@@ -129,6 +129,12 @@ def load() -> C.CDLL:
     lib.mjv_llm_prefill.argtypes = [vp, vp, C.POINTER(Batch), vp, vp, i64, vp]
     lib.mjv_reward_head.argtypes = [vp, vp, i32, C.POINTER(Outputs), vp, i64, vp]
     lib.mjv_score_forward.argtypes = [vp, C.POINTER(Batch), C.POINTER(Outputs), vp, i64, vp]
+    lib.mjv_comm_unique_id.argtypes = [vp]
+    lib.mjv_comm_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    lib.mjv_comm_destroy.argtypes = [vp]
+    lib.mjv_allgather_scores.argtypes = [vp, vp, i64, i32, vp, vp]
+    for name in ("mjv_comm_unique_id", "mjv_comm_create", "mjv_comm_destroy", "mjv_allgather_scores"):
+        getattr(lib, name).restype = C.c_int
     for name in ("mjv_layernorm", "mjv_pixel_shuffle_layernorm", "mjv_rmsnorm", "mjv_embed_tokens",
                  "mjv_im2col_patches", "mjv_preprocess_frames", "mjv_choose_grid", "mjv_bicubic_coeffs", "mjv_create",
                  "mjv_load_weight", "mjv_finalize_weights", "mjv_vit_forward", "mjv_project_and_splice",

@@ -27,6 +27,57 @@ def preference_decisions(scores: torch.Tensor) -> torch.Tensor:
     return (~(s[:, 0] > s[:, 1])).to(torch.int64)
 
 
+class NcclScoreGather:
+    """The C-ABI all-gather (`mjv_allgather_scores`, csrc/comm.cu): an NCCL communicator created by the library from a
+    unique id that rank 0 generates and torch.distributed (any backend) distributes once. `gather` is enqueued on the
+    current CUDA stream; it never synchronises the host."""
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self._C = _lib, C
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            _lib.check(self.lib.mjv_comm_unique_id(buf))
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        box = [ident]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = (C.c_ubyte * 128)(*box[0].tolist())
+        self._comm = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mjv_comm_create(raw, self.rank, self.world, C.byref(self._comm)))
+
+    def gather(self, local: torch.Tensor, n_pairs: int) -> torch.Tensor:
+        """local [2*pairs_local, W] fp32 CUDA -> [2*n_pairs, W] in pair order (same contract as allgather_scores)."""
+        per = (n_pairs + self.world - 1) // self.world
+        width = local.shape[1]
+        padded = torch.zeros((2 * per, width), dtype=torch.float32, device=self.device)
+        padded[: local.shape[0]] = local
+        out = torch.empty((self.world * 2 * per, width), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._lib.check(self.lib.mjv_allgather_scores(self._comm, padded.data_ptr(), 2 * per, width, out.data_ptr(),
+                                                          self._lib.current_stream()))
+        padded.record_stream(torch.cuda.current_stream(self.device))
+        rows = [out[r * 2 * per: r * 2 * per + 2 * len(shard_pairs(n_pairs, r, self.world))] for r in range(self.world)]
+        return torch.cat(rows)
+
+    def close(self):
+        if getattr(self, "_comm", None) is not None and self._comm.value:
+            self.lib.mjv_comm_destroy(self._comm)
+            self._comm = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 def allgather_scores(local: torch.Tensor, n_pairs: int, group=None) -> torch.Tensor:
     """All-gather the per-row score table. `local` is [2*pairs_local, W] fp32; returns [2*n_pairs, W] in pair order.
     Equal-count collective: every rank pads its block to 2*ceil(n_pairs/world) rows."""

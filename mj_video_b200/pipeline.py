@@ -60,7 +60,7 @@ class PairScorer:
     sampled frames of the clip, i.e. what `load_video` feeds to dynamic_preprocess) and prompt token ids."""
 
     def __init__(self, forward_fn, preprocess_fn, pad_token_id: int, rows_per_step: int = 32, max_num: int = 1,
-                 input_size: int = 448, device=None, group=None, prefetch: int = 2):
+                 input_size: int = 448, device=None, group=None, prefetch: int = 2, gather_fn=None):
         """forward_fn(pixel_values, input_ids, attention_mask) -> [rows, W] fp32 score table on `device`;
         preprocess_fn(frames_u8_device, input_size, max_num) -> (tiles, tiles_per_frame)."""
         if rows_per_step < 2 or rows_per_step % 2:
@@ -71,6 +71,8 @@ class PairScorer:
         self.device = torch.device(device) if device is not None else torch.device("cpu")
         self.group = group
         self.prefetch = max(1, prefetch)
+        # (local table, n_pairs) -> full table; default: torch.distributed all-gather (gloo on CPU, NCCL on GPU)
+        self.gather_fn = gather_fn or (lambda local, n: mdist.allgather_scores(local, n, group))
 
     @classmethod
     def for_engine(cls, engine, pad_token_id: int, img_context_token_id: int, **kw):
@@ -83,6 +85,10 @@ class PairScorer:
         def pre(frames_dev, input_size, max_num):
             return preprocess_frames(frames_dev, input_size, max_num, True, torch.bfloat16)
 
+        import torch.distributed as tdist
+        if "gather_fn" not in kw and tdist.is_available() and tdist.is_initialized() and \
+                tdist.get_world_size(kw.get("group")) > 1:
+            kw["gather_fn"] = mdist.NcclScoreGather(engine.device, kw.get("group")).gather  # C ABI: mjv_allgather_scores
         return cls(fwd, pre, pad_token_id, device=engine.device, **kw)
 
     # ------------------------------------------------------------------------------------------------
@@ -134,7 +140,7 @@ class PairScorer:
         if local is None:                                      # this rank owns no pair
             width = self._width_hint(dataset)
             local = torch.zeros((0, width), dtype=torch.float32, device=self.device)
-        table = mdist.allgather_scores(local, n_pairs, self.group)
+        table = self.gather_fn(local, n_pairs)
         return dict(scores=table, prefer=mdist.preference_decisions(table[:, -1]), rows_local=row0)
 
     def _stage(self, hb, copy_stream):
@@ -156,22 +162,29 @@ class PairScorer:
 
 
 class SyntheticPairs:
-    """Seeded synthetic preference pairs: pair k = videos (2k, 2k+1) under one caption."""
+    """Seeded synthetic preference pairs: pair k = videos (2k, 2k+1) under one caption.
+    `pool` > 0 generates that many distinct clips once and cycles through them (row r -> clip r % pool), so that a
+    throughput run measures the scoring pipeline rather than the numpy video generator (~0.3 s per clip)."""
     score_width = 34
 
     def __init__(self, n_pairs: int, n_frames: int = 8, height: int = 448, width: int = 448, tiles_per_frame: int = 1,
-                 first_video: int = 0):
+                 first_video: int = 0, pool: int = 0):
         self.n, self.n_frames, self.h, self.w, self.tpf, self.v0 = n_pairs, n_frames, height, width, tiles_per_frame, first_video
+        self.pool = [self._clip(i) for i in range(pool)] if pool > 0 else None
+
+    def _clip(self, r):
+        from . import synth
+        from .data_processor import get_index
+        vid = synth.make_video(self.v0 + r, n_frames=2 * self.n_frames, height=self.h, width=self.w)
+        return np.ascontiguousarray(vid[get_index(None, 8.0, len(vid) - 1, 0, self.n_frames)])
 
     def __len__(self):
         return self.n
 
     def __getitem__(self, k):
         from . import synth
-        from .data_processor import get_index
         out = []
         for r in (2 * k, 2 * k + 1):
-            vid = synth.make_video(self.v0 + r, n_frames=2 * self.n_frames, height=self.h, width=self.w)
-            idx = get_index(None, 8.0, len(vid) - 1, 0, self.n_frames)
-            out.append((vid[idx], synth.make_input_ids(k, [self.tpf] * self.n_frames)))
+            clip = self.pool[r % len(self.pool)] if self.pool else self._clip(r)
+            out.append((clip, synth.make_input_ids(k, [self.tpf] * self.n_frames)))
         return tuple(out)

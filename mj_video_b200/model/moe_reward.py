@@ -160,12 +160,19 @@ class InternVLChatRewardModeling(nn.Module):
                                "there is no CPU path")
         key = self._weights_key()
         if self._engine is None or self._engine.device != dev:
-            self._engine = Engine(_engine_dims(self.config), dev)
+            # a bf16 module mirrors the reference's `.to(bfloat16)` Llama branch, whose rotary inv_freq buffer is rounded too
+            self._engine = Engine(_engine_dims(self.config), dev,
+                                  rope_inv_freq_bf16=self.model.dtype == torch.bfloat16)
             self._engine_key = None
         if self._engine_key != key:
             self._engine.load_state_dict(self.state_dict())
             self._engine_key = key
         return self._engine
+
+    @property
+    def engine(self) -> Engine:
+        """The CUDA engine holding this module's current weights (built / refreshed on demand)."""
+        return self._get_engine()
 
     def forward(self, pixel_values: torch.FloatTensor, input_ids: torch.LongTensor = None,
                 attention_mask: Optional[torch.Tensor] = None, position_ids=None, image_flags=None,

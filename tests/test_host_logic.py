@@ -190,3 +190,32 @@ def test_pair_sharding():
     assert pair_rows(range(2, 4)) == [(4, 5), (6, 7)]                      # chosen/rejected stay together
     s = torch.tensor([0.3, 0.1, 0.2, 0.2, -1.0, 0.5])
     assert preference_decisions(s).tolist() == [0, 1, 1]                    # ~(s0 > s1): ties -> video_1
+
+
+def test_safetensors_checkpoint_roundtrip(tmp_path):
+    """weights travel as *.safetensors named by state-dict key (overall_train.py:503-522)."""
+    pytest.importorskip("safetensors")
+    import torch
+    from mj_video_b200 import checkpoint, synth
+    d = synth.dims_tiny()
+    sd = synth.make_state_dict(d, seed=4)
+    keys = sorted(sd)
+    checkpoint.save_state_dict({k: sd[k] for k in keys[: len(keys) // 2]}, str(tmp_path / "model-00001-of-00002.safetensors"))
+    checkpoint.save_state_dict({k: sd[k] for k in keys[len(keys) // 2:]}, str(tmp_path / "model-00002-of-00002.safetensors"))
+    got = dict(checkpoint.iter_tensors(str(tmp_path)))
+    assert sorted(got) == keys and all(torch.equal(got[k], sd[k]) for k in keys)
+
+    class FakeEngine:
+        def __init__(self):
+            self.keys, self.final = [], False
+
+        def load_weight(self, k, t):
+            self.keys.append(k)
+
+        def finalize(self):
+            self.final = True
+    fe = FakeEngine()
+    n = checkpoint.load_into_engine(fe, str(tmp_path))
+    assert fe.final and n == len(keys) - 1 and "model.language_model.output.weight" not in fe.keys
+    with pytest.raises(FileNotFoundError):
+        checkpoint.checkpoint_files(str(tmp_path / "missing"))

@@ -21,6 +21,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_OUT = sys.stdout
 METRIC = "video pairs scored/sec @8x448^2 frames"
 UNIT = "pairs/s"
 WORKLOAD = "MJ-VIDEO-2B bf16, batch of 32 synthetic text-video pairs per GPU, 8 frames 448^2, max_num=1 (BASELINE configs[1])"
@@ -171,7 +172,7 @@ def run_reference(args):
                 data="synthetic", config=dict(workload=WORKLOAD, sample=sample),
                 cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def run_mjv(args):
@@ -353,12 +354,23 @@ def run_mjv(args):
                     e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
                     gpu_launches=launches, clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline,
                     step_tflops=step_tflops, step_frac_of_sustained_peak=step_tflops / world / pk["sustained"])
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Route everything libraries print on fd 1 (NCCL prints its version banner there) to stderr; the ONE JSON line of
+    the contract is written to the original stdout through the returned file object."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global _OUT
+    _OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -381,7 +393,7 @@ def main():
             # convenience: re-launch under torchrun when called directly with --gpus N
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"), __file__] + sys.argv[1:]
-            sys.exit(subprocess.call(cmd))
+            sys.exit(subprocess.call(cmd, stdout=_OUT))
         run_mjv(args)
 
 

@@ -330,3 +330,26 @@ def test_pair_scorer_matches_direct_forward(tiny_engine, gpu):
     # micro-batch composition differs (4 rows vs 2 rows per launch) but rows are independent: tiny bf16-level differences
     assert (out["scores"] - ref).abs().max().item() < 1e-2
     assert torch.equal(out["prefer"].cpu(), preference_decisions(out["scores"][:, -1]).cpu())
+
+
+def test_text_only_row_and_surplus_tiles(tiny_engine, gpu):
+    """Edge cases the reference handles: a row without any <image> inside a batch, and a call with one tile more than the
+    prompt has <IMG_CONTEXT> slots for (warning + the first n_token visual embeddings, modeling_internvl_chat.py:178-186)."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from oracle import port
+    d, sd, eng = tiny_engine
+    pv = load_video(synth.make_video(21), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)[0]
+    text_only = [1, 92543] + list(range(2000, 2040)) + synth.GATING_PATTERN
+    ids, mask = synth.pad_batch([synth.make_input_ids(2, [1] * 8, n_cap=12), text_only])
+    mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
+    ref = port.Oracle(d, sd, dtype=torch.float32, device=gpu).forward(pv.float(), ids, mask)
+    _check(mine, ref)
+    pv9 = torch.cat([pv, pv[:1] * 0.5])
+    ids1, mask1 = synth.pad_batch([synth.make_input_ids(2, [1] * 8, n_cap=12)])
+    with pytest.warns(UserWarning, match="visual embeddings"):
+        mine = _as_dict(d, eng.forward(pv9, ids1, mask1, synth.PAD, synth.IMG_CONTEXT))
+    ref = port.Oracle(d, sd, dtype=torch.float32, device=gpu).forward(pv9.float(), ids1, mask1)
+    _check(mine, ref)
+    with pytest.raises(RuntimeError, match="IMG_CONTEXT"):      # fewer embeddings than slots: the reference raises too
+        eng.forward(pv[:7], ids1, mask1, synth.PAD, synth.IMG_CONTEXT)

@@ -55,6 +55,26 @@ def test_first_slot_layout(ref_model):
         assert torch.equal(ref[k].float(), out[k].float()), k
 
 
+def test_text_only_row_and_surplus_tiles(ref_model, capsys):
+    """A batch whose second row has no <image> at all, and a call with one tile more than the prompt has room for (the
+    reference prints a warning and keeps the first n_token visual embeddings, modeling_internvl_chat.py:178-186)."""
+    d, sd, m, rh = ref_model
+    pv = rh.reference_load_video(synth.make_video(21), num_segments=8, max_num=1)[0]
+    text_only = [1, 92543] + list(range(2000, 2040)) + synth.GATING_PATTERN
+    ids, mask = synth.pad_batch([synth.make_input_ids(2, [1] * 8, n_cap=12), text_only])
+    ref = rh.reference_forward(m, pv, ids, mask)
+    out = port.Oracle(d, sd).forward(pv, ids, mask)
+    for k in ref:
+        assert torch.equal(ref[k].float(), out[k].float()), k
+    pv9 = torch.cat([pv, pv[:1] * 0.5])
+    ids1, mask1 = synth.pad_batch([synth.make_input_ids(2, [1] * 8, n_cap=12)])
+    ref = rh.reference_forward(m, pv9, ids1, mask1)
+    assert "warning" in capsys.readouterr().out
+    out = port.Oracle(d, sd).forward(pv9, ids1, mask1)
+    for k in ref:
+        assert torch.equal(ref[k].float(), out[k].float()), k
+
+
 def test_reference_errors(ref_model):
     d, sd, m, rh = ref_model
     pv = torch.zeros(8, 3, 448, 448)

@@ -27,71 +27,98 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
                       ptx::pack_bf16x2(f[6], f[7]));
 }
 
+// Sum over the W warps that share a row (W = 1: plain warp reduction). Every thread of the block must call it.
+template <int W>
+__device__ __forceinline__ float row_sum(float v, float* red, int warp_in_block) {
+    v = warp_sum(v);
+    if (W == 1) return v;
+    __syncthreads();  // previous use of `red` is over
+    if ((threadIdx.x & 31) == 0) red[warp_in_block] = v;
+    __syncthreads();
+    float t = 0.f;
+    const int base = warp_in_block / W * W;
+#pragma unroll
+    for (int i = 0; i < W; ++i) t += red[base + i];
+    return t;
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // out[r,:] = bf16((x - mean) * rstd * w + b) over C columns (nn.LayerNorm: modeling_intern_vit.py:291,293; mlp1.0
 // modeling_internvl_chat.py:136). GATHER: the row is assembled from 4 source rows of C/4 columns (pixel_shuffle v2,
 // modeling_internvl_chat.py:228-262): out row (t, i, j), column b*C/2 + a*C/4 + c  <-  x[t, 1 + (2i+b)*G + (2j+a), c].
-template <int NCHUNK, bool GATHER>
+// W warps share a row (wide rows keep <= 4 16-byte chunks per thread, so many blocks stay resident); the row is held
+// packed (bf16) in registers between the passes.
+template <int NCHUNK, int W, bool GATHER>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                  const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, long long rows, int C, float eps,
                  long long ldx, int grid_g, int seq) {
-    const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    __shared__ float red[kWarpsPerBlock];
+    const int wib = threadIdx.x >> 5;
+    const long long row = static_cast<long long>(blockIdx.x) * (kWarpsPerBlock / W) + wib / W;
+    const int wsub = wib % W;
+    const bool active = row < rows;
     const int lane = threadIdx.x & 31;
-    float v[NCHUNK][8];
-    float sum = 0.f;
+    uint4 u[NCHUNK];
+    long long g_base = 0;
+    int cq = 1;
+    if (GATHER && active) {
+        const int half = grid_g / 2;
+        const int per_tile = half * half;
+        const long long t = row / per_tile;
+        const int ij = static_cast<int>(row - t * per_tile);
+        const int i = ij / half, j = ij - i * half;
+        cq = C / 4;
+        g_base = t * seq + 1 + static_cast<long long>(2 * i) * grid_g + 2 * j;
+    }
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
-        const int c = ch * 256 + lane * 8;
-        if (c < C) {
+        const int c = (ch * W + wsub) * 256 + lane * 8;
+        u[ch] = make_uint4(0u, 0u, 0u, 0u);
+        if (active && c < C) {
             const __nv_bfloat16* src;
             if (GATHER) {
-                const int half = grid_g / 2;
-                const int per_tile = half * half;
-                const long long t = row / per_tile;
-                const int ij = static_cast<int>(row - t * per_tile);
-                const int i = ij / half, j = ij - i * half;
-                const int cq = C / 4;
                 const int blk = c / cq;  // b*2 + a
-                const int cc = c - blk * cq;
-                const int bb = blk >> 1, aa = blk & 1;
-                src = x + (t * seq + 1 + (2 * i + bb) * grid_g + (2 * j + aa)) * ldx + cc;
+                src = x + (g_base + (blk >> 1) * grid_g + (blk & 1)) * ldx + (c - blk * cq);
             } else {
                 src = x + row * ldx + c;
             }
-            const uint4 u = *reinterpret_cast<const uint4*>(src);
-            unpack8(u, v[ch]);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) sum += v[ch][e];
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[ch][e] = 0.f;
+            u[ch] = *reinterpret_cast<const uint4*>(src);
         }
     }
-    const float mean = warp_sum(sum) / static_cast<float>(C);
+    float sum = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+        float f[8];
+        unpack8(u[ch], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += f[e];  // chunks beyond C hold zeros
+    }
+    const float mean = row_sum<W>(sum, red, wib) / static_cast<float>(C);
     float sq = 0.f;
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
-        const int c = ch * 256 + lane * 8;
-        if (c < C) {
+        if ((ch * W + wsub) * 256 + lane * 8 < C) {
+            float f[8];
+            unpack8(u[ch], f);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float dlt = v[ch][e] - mean;
+                const float dlt = f[e] - mean;
                 sq += dlt * dlt;
             }
         }
     }
-    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(C) + eps);
+    const float rstd = rsqrtf(row_sum<W>(sq, red, wib) / static_cast<float>(C) + eps);
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
-        const int c = ch * 256 + lane * 8;
-        if (c < C) {
-            float wf[8], bf[8], o[8];
+        const int c = (ch * W + wsub) * 256 + lane * 8;
+        if (active && c < C) {
+            float f[8], wf[8], bf[8], o[8];
+            unpack8(u[ch], f);
             unpack8(__ldg(reinterpret_cast<const uint4*>(w + c)), wf);
             unpack8(__ldg(reinterpret_cast<const uint4*>(b + c)), bf);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = (v[ch][e] - mean) * rstd * wf[e] + bf[e];
+            for (int e = 0; e < 8; ++e) o[e] = (f[e] - mean) * rstd * wf[e] + bf[e];
             *reinterpret_cast<uint4*>(out + row * C + c) = pack8(o);
         }
     }
@@ -100,34 +127,41 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
 // ------------------------------------------------------------------------------------------------ RMSNorm
 // InternLM2RMSNorm (modeling_internlm2.py:138-143): y = bf16(x * rsqrt(mean(x^2) + eps)); out = bf16(w * y).
 // row_idx (optional) gathers source rows, so the final norm runs only on the 2 rows per sample the head reads.
-template <int NCHUNK>
+template <int NCHUNK, int W>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                __nv_bfloat16* __restrict__ out, long long rows, int C, float eps, const int* __restrict__ row_idx) {
-    const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    __shared__ float red[kWarpsPerBlock];
+    const int wib = threadIdx.x >> 5;
+    const long long row = static_cast<long long>(blockIdx.x) * (kWarpsPerBlock / W) + wib / W;
+    const int wsub = wib % W;
+    const bool active = row < rows;
     const int lane = threadIdx.x & 31;
-    const long long srow = row_idx != nullptr ? row_idx[row] : row;
-    float v[NCHUNK][8];
+    const long long srow = active ? (row_idx != nullptr ? row_idx[row] : row) : 0;
+    uint4 u[NCHUNK];  // the row stays packed (bf16) in registers between the two passes
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int c = (ch * W + wsub) * 256 + lane * 8;
+        u[ch] = (active && c < C) ? *reinterpret_cast<const uint4*>(x + srow * C + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
     float sq = 0.f;
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
-        const int c = ch * 256 + lane * 8;
-        if (c < C) {
-            unpack8(*reinterpret_cast<const uint4*>(x + srow * C + c), v[ch]);
+        float f[8];
+        unpack8(u[ch], f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) sq += v[ch][e] * v[ch][e];
-        }
+        for (int e = 0; e < 8; ++e) sq += f[e] * f[e];
     }
-    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(C) + eps);
+    const float rstd = rsqrtf(row_sum<W>(sq, red, wib) / static_cast<float>(C) + eps);
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
-        const int c = ch * 256 + lane * 8;
-        if (c < C) {
-            float wf[8], o[8];
+        const int c = (ch * W + wsub) * 256 + lane * 8;
+        if (active && c < C) {
+            float f[8], wf[8], o[8];
+            unpack8(u[ch], f);
             unpack8(__ldg(reinterpret_cast<const uint4*>(w + c)), wf);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = wf[e] * ptx::bf16_round(v[ch][e] * rstd);
+            for (int e = 0; e < 8; ++e) o[e] = wf[e] * ptx::bf16_round(f[e] * rstd);
             *reinterpret_cast<uint4*>(out + row * C + c) = pack8(o);
         }
     }
@@ -164,36 +198,57 @@ gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict_
 // ------------------------------------------------------------------------------------------------ patch im2col
 // pixel_values [T,3,H,W] (bf16 or fp32) -> A[T*P, Kpad] bf16 with k = c*ps*ps + ky*ps + kx (the flattening of
 // nn.Conv2d's weight, modeling_intern_vit.py:164), zero padded to Kpad so rows are 16-byte aligned for TMA.
+// One block = one row of patches of one tile: the 3 x ps image rows it covers are staged in shared memory with coalesced
+// 16-byte loads (each image row is contiguous), then every thread assembles 8 consecutive k of one patch from shared
+// memory and issues one 16-byte store — both global streams are fully coalesced.
 template <typename TIn>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 im2col_kernel(const TIn* __restrict__ px, __nv_bfloat16* __restrict__ out, int T, int img, int ps, int Kpad) {
-    // one thread = 8 consecutive k of one patch row of A (one 16-byte store); 32-bit index arithmetic throughout
+    extern __shared__ __align__(16) unsigned char im2col_smem[];
+    __nv_bfloat16* rows_s = reinterpret_cast<__nv_bfloat16*>(im2col_smem);  // [3][ps][img]
     const int g = img / ps;
     const int K = 3 * ps * ps;
     const int kvec = Kpad / 8;
-    const unsigned total = static_cast<unsigned>(T) * g * g * kvec;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const unsigned p = i / kvec;          // patch index over all tiles
-        const int k0 = (i - p * kvec) * 8;
-        const unsigned tp = p / g;
-        const int pj = p - tp * g;
-        const unsigned t = tp / g;
-        const int pi = tp - t * g;
-        const TIn* base = px + (static_cast<size_t>(t) * 3 * img + pi * ps) * img + pj * ps;
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int k = k0 + e;
-            float val = 0.f;
-            if (k < K) {
-                const int c = k / (ps * ps);
-                const int rem = k - c * ps * ps;
-                const int ky = rem / ps, kx = rem - ky * ps;
-                val = static_cast<float>(base[(static_cast<size_t>(c) * img + ky) * img + kx]);
-            }
-            f[e] = val;
+    const int t = blockIdx.x / g, pi = blockIdx.x - t * g;
+    constexpr int VEC = 16 / sizeof(TIn);  // elements per 16-byte load
+    const int vec_per_row = img / VEC;
+    const int n_vec = 3 * ps * vec_per_row;
+    for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+        const int r = i / vec_per_row, v = i - r * vec_per_row;  // r = c*ps + ky
+        const int c = r / ps, ky = r - c * ps;
+        const TIn* src = px + ((static_cast<size_t>(t) * 3 + c) * img + pi * ps + ky) * img + v * VEC;
+        const uint4 raw = *reinterpret_cast<const uint4*>(src);
+        __nv_bfloat16* dst = rows_s + r * img + v * VEC;
+        if (sizeof(TIn) == 2) {
+            *reinterpret_cast<uint4*>(dst) = raw;
+        } else {
+            const float* f = reinterpret_cast<const float*>(&raw);
+            *reinterpret_cast<uint2*>(dst) = make_uint2(ptx::pack_bf16x2(f[0], f[1]), ptx::pack_bf16x2(f[2], f[3]));
         }
-        *reinterpret_cast<uint4*>(out + static_cast<size_t>(p) * Kpad + k0) = pack8(f);
+    }
+    __syncthreads();
+    // blockDim.x is a multiple of kvec: a thread always produces the same 8 k of successive patches, so the k -> (row,
+    // column) decomposition (integer divisions) is done once, outside the loop
+    const int kv = threadIdx.x % kvec;
+    const int k0 = kv * 8;
+    int off[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e;
+        const int r = k / ps;  // c*ps + ky
+        off[e] = k < K ? r * img + (k - r * ps) : -1;
+    }
+    const unsigned short* rs = reinterpret_cast<const unsigned short*>(rows_s);
+    for (int pj = threadIdx.x / kvec; pj < g; pj += blockDim.x / kvec) {
+        uint32_t packed[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            const unsigned short lo = off[e] >= 0 ? rs[off[e] + pj * ps] : 0;
+            const unsigned short hi = off[e + 1] >= 0 ? rs[off[e + 1] + pj * ps] : 0;
+            packed[e >> 1] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+        }
+        const size_t p = (static_cast<size_t>(t) * g + pi) * g + pj;
+        *reinterpret_cast<uint4*>(out + p * Kpad + k0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
 }
 
@@ -206,20 +261,23 @@ __global__ void cls_rows_kernel(const __nv_bfloat16* __restrict__ cls, const __n
     hidden[static_cast<long long>(t) * S * C + c] = __float2bfloat16_rn(__bfloat162float(cls[c]) + __bfloat162float(pos[c]));
 }
 
+// rows up to 1024 columns: one warp per row; wider rows: 2 or 4 warps per row with <= 4 chunks per thread
 template <bool GATHER>
 int launch_ln(const __nv_bfloat16* x, const __nv_bfloat16* w, const __nv_bfloat16* b, __nv_bfloat16* out,
               long long rows, int C, float eps, long long ldx, int grid_g, int seq, cudaStream_t st) {
     MJV_CHECK(C % 8 == 0 && C <= 4096, MJV_ERR_ARG, "layernorm: C=%d unsupported", C);
     const int nchunk = (C + 255) / 256;
-    const unsigned grid = static_cast<unsigned>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const int wpr = nchunk <= 4 ? 1 : (nchunk <= 8 ? 2 : 4);
+    const int rows_per_block = kWarpsPerBlock / wpr;
+    const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
     const int threads = kWarpsPerBlock * 32;
     LaunchScope scope(GATHER ? TAG_PIXSHUF_LN : TAG_LAYERNORM, st, 4.0 * rows * C);
-#define MJV_LN(NC) layernorm_kernel<NC, GATHER><<<grid, threads, 0, st>>>(x, w, b, out, rows, C, eps, ldx, grid_g, seq)
-    if (nchunk <= 1) MJV_LN(1);
-    else if (nchunk <= 2) MJV_LN(2);
-    else if (nchunk <= 4) MJV_LN(4);
-    else if (nchunk <= 8) MJV_LN(8);
-    else MJV_LN(16);
+#define MJV_LN(NC, W) layernorm_kernel<NC, W, GATHER><<<grid, threads, 0, st>>>(x, w, b, out, rows, C, eps, ldx, grid_g, seq)
+    if (nchunk <= 1) MJV_LN(1, 1);
+    else if (nchunk <= 2) MJV_LN(2, 1);
+    else if (nchunk <= 4) MJV_LN(4, 1);
+    else if (nchunk <= 8) MJV_LN(4, 2);
+    else MJV_LN(4, 4);
 #undef MJV_LN
     MJV_CUDA_OK(cudaGetLastError());
     return 0;
@@ -251,16 +309,18 @@ int rmsnorm(const void* x, const void* w, void* out, long long rows, int C, floa
     if (rows == 0) return 0;
     MJV_CHECK(C % 8 == 0 && C <= 4096, MJV_ERR_ARG, "rmsnorm: C=%d unsupported", C);
     const int nchunk = (C + 255) / 256;
-    const unsigned grid = static_cast<unsigned>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const int wpr = nchunk <= 4 ? 1 : (nchunk <= 8 ? 2 : 4);
+    const int rows_per_block = kWarpsPerBlock / wpr;
+    const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
     const int threads = kWarpsPerBlock * 32;
     LaunchScope scope(TAG_RMSNORM, st, 4.0 * rows * C);
-#define MJV_RMS(NC) \
-    rmsnorm_kernel<NC><<<grid, threads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)out, rows, C, eps, row_idx)
-    if (nchunk <= 1) MJV_RMS(1);
-    else if (nchunk <= 2) MJV_RMS(2);
-    else if (nchunk <= 4) MJV_RMS(4);
-    else if (nchunk <= 8) MJV_RMS(8);
-    else MJV_RMS(16);
+#define MJV_RMS(NC, W) \
+    rmsnorm_kernel<NC, W><<<grid, threads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)out, rows, C, eps, row_idx)
+    if (nchunk <= 1) MJV_RMS(1, 1);
+    else if (nchunk <= 2) MJV_RMS(2, 1);
+    else if (nchunk <= 4) MJV_RMS(4, 1);
+    else if (nchunk <= 8) MJV_RMS(4, 2);
+    else MJV_RMS(4, 4);
 #undef MJV_RMS
     MJV_CUDA_OK(cudaGetLastError());
     return 0;
@@ -294,14 +354,26 @@ int embed_tokens(const int* ids, const void* table, void* out, long long rows, i
 
 int im2col_patches(const void* px, int px_dtype, void* out, int T, int img, int ps, int Kpad, cudaStream_t st) {
     if (T == 0) return 0;
-    MJV_CHECK(img % ps == 0 && Kpad >= 3 * ps * ps && Kpad % 8 == 0, MJV_ERR_ARG, "im2col: bad geometry");
-    const int grid = sm_count() * 8;
+    MJV_CHECK(img % ps == 0 && Kpad >= 3 * ps * ps && Kpad % 8 == 0 && img % 8 == 0, MJV_ERR_ARG, "im2col: bad geometry");
+    MJV_CHECK((reinterpret_cast<uintptr_t>(px) & 15) == 0, MJV_ERR_ARG, "im2col: pixel_values must be 16-byte aligned");
     const int g_ = img / ps;
+    const int grid = T * g_;
+    const size_t smem = static_cast<size_t>(3) * ps * img * sizeof(__nv_bfloat16);
+    MJV_CHECK(smem <= 200 * 1024, MJV_ERR_ARG, "im2col: image rows do not fit in shared memory");
+    const int kvec = Kpad / 8;
+    MJV_CHECK(kvec <= 512, MJV_ERR_ARG, "im2col: Kpad %d too large", Kpad);
+    const int threads = kvec * (kvec >= 384 ? 1 : 384 / kvec);  // a multiple of kvec, ~384 threads
+    static bool configured = false;
+    if (!configured) {
+        MJV_CUDA_OK(cudaFuncSetAttribute(im2col_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MJV_CUDA_OK(cudaFuncSetAttribute(im2col_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
     LaunchScope scope(TAG_IM2COL, st, (double)T * (3.0 * img * img * (px_dtype == MJV_DTYPE_F32 ? 4 : 2) + 2.0 * g_ * g_ * Kpad));
     if (px_dtype == MJV_DTYPE_BF16)
-        im2col_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)px, (__nv_bfloat16*)out, T, img, ps, Kpad);
+        im2col_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>((const __nv_bfloat16*)px, (__nv_bfloat16*)out, T, img, ps, Kpad);
     else if (px_dtype == MJV_DTYPE_F32)
-        im2col_kernel<float><<<grid, 256, 0, st>>>((const float*)px, (__nv_bfloat16*)out, T, img, ps, Kpad);
+        im2col_kernel<float><<<grid, threads, smem, st>>>((const float*)px, (__nv_bfloat16*)out, T, img, ps, Kpad);
     else
         return set_error(MJV_ERR_ARG, "im2col: unsupported pixel dtype %d", px_dtype);
     MJV_CUDA_OK(cudaGetLastError());

@@ -194,16 +194,23 @@ def test_preference_decisions_tiny(tiny_engine, gpu):
     assert agree_decided == 1.0 and agree >= 0.9, (agree, agree_decided, margin.min().item())
 
 
-def test_full_size_2b_row_vs_oracle(gpu):
-    """BASELINE configs[0]/[1] shapes: MJ-VIDEO-2B, 2 rows x 8 frames, against the oracle in fp32 and bf16 on the GPU."""
+@pytest.fixture(scope="module")
+def full_engine(gpu):
     from mj_video_b200 import synth
-    from mj_video_b200.data_processor import load_video
     from mj_video_b200.engine import Engine, EngineDims
-    from oracle import port
     d = synth.dims_2b()
     sd = synth.make_state_dict(d, seed=1234, include_lm_head=False)
     eng = Engine(EngineDims.from_synth(d), gpu)
     eng.load_state_dict(sd)
+    return d, sd, eng
+
+
+def test_full_size_2b_row_vs_oracle(full_engine, gpu):
+    """BASELINE configs[0]/[1] shapes: MJ-VIDEO-2B, 2 rows x 8 frames, against the oracle in fp32 and bf16 on the GPU."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from oracle import port
+    d, sd, eng = full_engine
     pv = torch.cat([load_video(synth.make_video(i), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)[0]
                     for i in range(2)])
     ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8), synth.make_input_ids(0, [1] * 8)])
@@ -221,6 +228,31 @@ def test_full_size_2b_row_vs_oracle(gpu):
     # same caption, two different videos -> the decision matches the oracle's
     s, r = mine["score"].float().cpu(), o32["score"].float().cpu()
     assert (s[0] > s[1]) == (r[0] > r[1]) or abs(r[0] - r[1]) < 5e-3
+    del o32
+    torch.cuda.empty_cache()
+
+
+def test_full_size_large_batch_rows_are_independent(full_engine, gpu):
+    """Maximum-size case: 96 rows (768 tiles, ~211k tokens, >2^31-element activation matrices) in ONE call. Rows are
+    independent in the reference (per-tile ViT, per-sequence attention), so a row scores the same wherever it sits in
+    whatever batch: compared with the same rows scored 4 at a time."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    d, sd, eng = full_engine
+    clips = [load_video(synth.make_video(40 + i), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)[0]
+             for i in range(4)]
+    caps = [synth.make_input_ids(c, [1] * 8, n_cap=20 + 25 * c) for c in range(3)]
+    B = 96
+    rows = [caps[i % 3] for i in range(B)]
+    pv = torch.cat([clips[i % 4] for i in range(B)])
+    ids, mask = synth.pad_batch(rows)
+    big = eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT)["scores"].float().cpu()
+    assert torch.isfinite(big).all()
+    # (clip, caption) repeats every 12 rows: identical inputs at different batch positions give identical bits
+    assert torch.equal(big[:12], big[12:24]) and torch.equal(big[:12], big[84:96])
+    ids4, mask4 = synth.pad_batch(rows[:4])
+    small = eng.forward(pv[:32], ids4, mask4, synth.PAD, synth.IMG_CONTEXT)["scores"].float().cpu()
+    assert (small - big[:4]).abs().max().item() <= 2e-3, (small - big[:4]).abs().max().item()
 
 
 def test_long_visual_sequence_config4_shapes(tiny_engine, gpu):

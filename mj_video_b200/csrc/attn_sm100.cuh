@@ -8,11 +8,12 @@
 //   softmax    : 128 threads, one query row each (TMEM lane == row): ONE tcgen05.ld pass brings the 64 scores of the
 //                row into registers, row max, p = exp2(s·c − m) with packed fp32x2 math; P (bf16) is written BACK INTO
 //                TMEM over the S buffer it came from (tcgen05.st), one barrier arrival per warp        -> p_full
-//   MMA thread : O += P_j·V_j (A = P from TMEM, B = Vᵀ tile from smem, accumulator stays in TMEM)     -> pv_done, v_empty
+//   MMA thread : O += P_j·V_j (A = P from TMEM, B = Vᵀ tile from smem, accumulator stays in TMEM)     -> v_empty
 //                (tcgen05.mma executes in issue order, so S_{j+2} cannot overwrite P_j before P_j·V_j has read it)
 // so the softmax of block j+1 starts as soon as block j's P is handed over, while P_j·V_j runs on the tensor pipe.
 // The output accumulator never leaves TMEM until the end; the running max is updated lazily (only when it grows by more
-// than 2^8), in which case O is rescaled in place with tcgen05.ld/st after waiting for the P·V in flight (pv_done).
+// than 2^8), in which case O is rescaled in place with tcgen05.ld/st after waiting for the P·V in flight (the v_empty
+// barrier of its V tile, which the same tcgen05.commit signals).
 // PERSISTENT: the grid is 2 CTAs per SM; every CTA walks a static list of (sequence, head, query-block) items. The TMA and
 // MMA roles run ahead into the next item (Q double-buffered for head_dim 64, K/V ring and S ring shared across items) and
 // the output accumulator is handed over with o_done / o_empty, so barrier init, TMEM allocation, descriptor prefetch and
@@ -125,8 +126,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint64_t* v_empty = v_full + VS;         // [VS]  V tile consumed by its P·V MMA
     uint64_t* s_full = v_empty + VS;         // [3]
     uint64_t* p_full = s_full + 3;           // [3], one per S/P buffer
-    uint64_t* pv_done = p_full + 3;          // [2], alternating per step
-    uint64_t* o_done = pv_done + 2;          // accumulator of an item complete (MMA -> softmax)
+    uint64_t* o_done = p_full + 3;           // accumulator of an item complete (MMA -> softmax)
     uint64_t* o_empty = o_done + 1;          // accumulator read out (softmax -> MMA)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
 
@@ -147,7 +147,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(&q_full[b], 1);
             ptx::mbar_init(&q_empty[b], 1);
-            ptx::mbar_init(&pv_done[b], 1);
         }
         for (int b = 0; b < 3; ++b) ptx::mbar_init(&p_full[b], 4);  // one arrival per softmax warp
         for (int s = 0; s < KS; ++s) {
@@ -277,7 +276,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         ptx::mma_bf16_ts(tmem_O, p_tmem + ks * 8, b, idesc_o, (j | ks) != 0 ? 1u : 0u);
                     }
                     ptx::mma_commit(&v_empty[st]);
-                    ptx::mma_commit(&pv_done[g & 1]);
                     if (++st == VS) {
                         st = 0;
                         ph ^= 1;
@@ -348,9 +346,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         need = true;
                     }
                     if (__any_sync(0xffffffffu, need)) {
-                        // P·V_{g-1} must have landed in O. s_full_g already implies P·V_{g-NSB} retired, so the alternating
-                        // barrier is at most one of its phases behind and the parity wait cannot alias.
-                        ptx::mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+                        // P·V_{g-1} must have landed in O: its commit completes the v_empty barrier of the V tile it read
+                        // (ring slot (g-1) % VS, phase (g-1) / VS). That slot's NEXT completion belongs to P·V_{g-1+VS}, which
+                        // cannot be issued before this warp hands over P_g (VS >= 2), so the parity wait cannot alias.
+                        ptx::mbar_wait(&v_empty[(g - 1) % VS], ((g - 1) / VS) & 1);
                         ptx::tc_fence_after();
                         l_run *= alpha;
 #pragma unroll 1

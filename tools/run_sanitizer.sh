@@ -1,5 +1,8 @@
 #!/bin/bash
-# compute-sanitizer memcheck over one tiny forward (every kernel of the path) + the full GPU suite
+# compute-sanitizer (memcheck, initcheck, synccheck, racecheck) over one small forward that launches every kernel of the
+# path: resize + tiling frame kernels (4 tiles + thumbnail), ViT, projector/splice, LLM prefill with ragged rows, head.
+# Logs -> gpurun_out/sanitizer_<tool>.log (copied to profiles/r01_compute_sanitizer_<tool>.log).
+mkdir -p gpurun_out
 cat > /tmp/tiny_fwd.py <<'PY'
 import torch, sys
 sys.path.insert(0, ".")
@@ -17,5 +20,7 @@ out = eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT)
 torch.cuda.synchronize()
 print("scores", out["scores"][:, -1].tolist(), "tiles", pv.shape[0])
 PY
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 7 --launch-timeout 0 python /tmp/tiny_fwd.py > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -6 gpurun_out/sanitizer_memcheck.log
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+for tool in memcheck initcheck synccheck racecheck; do
+  timeout 1500 compute-sanitizer --tool $tool --error-exitcode 7 --launch-timeout 0 python /tmp/tiny_fwd.py > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "$tool rc=$?"; tail -3 gpurun_out/sanitizer_$tool.log
+done

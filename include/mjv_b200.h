@@ -236,6 +236,12 @@ int mjv_llm_prefill(mjv_handle* h, void* embeds_inout, const mjv_batch* batch, v
                     void* workspace, int64_t workspace_bytes, void* stream);
 int mjv_reward_head(mjv_handle* h, const void* gathered_2b, int32_t n_rows, const mjv_outputs* out, void* workspace,
                     int64_t workspace_bytes, void* stream);
+/* GatingNetwork as a standalone operator (moe_reward.py:16-42): which = 0 aspect_gating, 1 criteria_gating;
+ * x [n_rows, llm_hidden] bf16 -> out [n_rows, num_aspects | num_objectives] bf16: softmax(MLP(x) / T) * logit_scale
+ * (GatingNetwork.forward, :29-36) or the raw logits when with_softmax = 0 (forward_wo_softmax, :38-42).
+ * workspace: >= mjv_workspace_bytes(h, n_rows, 0, 0). */
+int mjv_gating_forward(mjv_handle* h, int32_t which, const void* x, int32_t n_rows, int32_t with_softmax, void* out,
+                       void* workspace, int64_t workspace_bytes, void* stream);
 /* the whole forward: ViT -> projector -> splice -> LLM prefill -> head */
 int mjv_score_forward(mjv_handle* h, const mjv_batch* batch, const mjv_outputs* out, void* workspace,
                       int64_t workspace_bytes, void* stream);

@@ -129,6 +129,8 @@ def load() -> C.CDLL:
     lib.mjv_llm_prefill.argtypes = [vp, vp, C.POINTER(Batch), vp, vp, i64, vp]
     lib.mjv_reward_head.argtypes = [vp, vp, i32, C.POINTER(Outputs), vp, i64, vp]
     lib.mjv_score_forward.argtypes = [vp, C.POINTER(Batch), C.POINTER(Outputs), vp, i64, vp]
+    lib.mjv_gating_forward.argtypes = [vp, i32, vp, i32, i32, vp, vp, i64, vp]
+    lib.mjv_gating_forward.restype = C.c_int
     lib.mjv_comm_unique_id.argtypes = [vp]
     lib.mjv_comm_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
     lib.mjv_comm_destroy.argtypes = [vp]

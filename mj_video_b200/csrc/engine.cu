@@ -721,6 +721,42 @@ int reward_head(mjv_handle* h, const void* gathered, int B, const mjv_outputs& o
     return 0;
 }
 
+// GatingNetwork as a standalone operator (moe_reward.py:16-42): n_hidden x (Linear + ReLU), Linear, then either the raw
+// logits (forward_wo_softmax) or softmax(x / T) * logit_scale (forward). x: [B, llm_hidden] bf16.
+int gating_forward(mjv_handle* h, int which, const void* x, int B, int with_softmax, void* out, Arena& ar, cudaStream_t st) {
+    const mjv_config& c = h->cfg;
+    MJV_CHECK(which == 0 || which == 1, MJV_ERR_ARG, "gating_forward: network %d (0 = aspect, 1 = criteria)", which);
+    const GateW& g = which == 0 ? h->aspect : h->criteria;
+    const int n_out = which == 0 ? c.num_aspects : c.num_objectives;
+    const int GH = c.gating_hidden, nh = c.gating_n_hidden;
+    __nv_bfloat16* buf[2];
+    for (int i = 0; i < 2; ++i) {
+        MJV_ALLOC(b_, __nv_bfloat16*, ar, static_cast<size_t>(B) * GH * 2);
+        buf[i] = b_;
+    }
+    MJV_ALLOC(logits, __nv_bfloat16*, ar, static_cast<size_t>(B) * 32 * 2);
+    const void* in = x;
+    int in_dim = c.llm_hidden;
+    for (int l = 0; l <= nh; ++l) {
+        const bool last = (l == nh);
+        HeadJobs jobs;
+        memset(&jobs, 0, sizeof(jobs));
+        HeadJob& j = jobs.j[0];
+        j.x = in; j.w = g.w[l]; j.bias = g.b[l];
+        j.y = last ? (with_softmax ? static_cast<void*>(logits) : out) : static_cast<void*>(buf[l & 1]);
+        j.N = last ? n_out : GH; j.K = in_dim; j.ldx = in_dim;
+        j.ldy = last ? (with_softmax ? 32 : n_out) : GH;
+        j.relu = last ? 0 : 1;
+        jobs.n = 1;
+        MJV_PROPAGATE(skinny_linear(jobs, B, st));
+        in = buf[l & 1];
+        in_dim = GH;
+    }
+    if (with_softmax)
+        MJV_PROPAGATE(gating_softmax(logits, 32, n_out, c.gating_temperature, g.logit_scale, out, n_out, B, st));
+    return 0;
+}
+
 int check_ready(const mjv_handle* h) {
     MJV_CHECK(h != nullptr, MJV_ERR_ARG, "null handle");
     MJV_CHECK(h->finalized, MJV_ERR_STATE, "weights not finalized: call mjv_finalize_weights first");
@@ -790,6 +826,14 @@ extern "C" int64_t mjv_workspace_bytes(const mjv_handle* h, int32_t n_rows, int3
     t2 = head_temp_bytes(h->cfg, n_rows);
     if (t2 > temp) temp = t2;
     return static_cast<int64_t>(persistent + temp + 65536);
+}
+
+extern "C" int mjv_gating_forward(mjv_handle* h, int32_t which, const void* x, int32_t n_rows, int32_t with_softmax,
+                                  void* out, void* workspace, int64_t workspace_bytes, void* stream) {
+    MJV_PROPAGATE(check_ready(h));
+    MJV_CHECK(x != nullptr && out != nullptr && n_rows >= 0, MJV_ERR_ARG, "mjv_gating_forward: bad arguments");
+    Arena ar(workspace, static_cast<size_t>(workspace_bytes));
+    return gating_forward(h, which, x, n_rows, with_softmax, out, ar, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mjv_vit_forward(mjv_handle* h, const void* pixel_values, int32_t pixel_dtype, int32_t n_tiles,

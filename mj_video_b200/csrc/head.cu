@@ -203,7 +203,42 @@ head_finalize_kernel(const HeadFinalizeArgs a) {
     }
 }
 
+// GatingNetwork.forward tail (moe_reward.py:33-36): softmax(x / T, dim=1) * logit_scale[0], one warp per row, n <= 32,
+// with the reference's bf16 rounding points (x / T, the softmax output and the product are bf16 tensors there).
+__global__ void __launch_bounds__(128)
+gating_softmax_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int n, float temperature,
+                      const __nv_bfloat16* __restrict__ logit_scale, __nv_bfloat16* __restrict__ out, int ldo, int B) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B) return;
+    const int lane = threadIdx.x & 31;
+    float x = -INFINITY;
+    if (lane < n) x = ptx::bf16_round(__bfloat162float(logits[row * ld + lane]) / temperature);
+    float mx = x;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    const float e = lane < n ? expf(x - mx) : 0.f;
+    float sum = e;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+    if (lane < n)
+        out[row * ldo + lane] = __float2bfloat16_rn(ptx::bf16_round(e / sum) * __bfloat162float(logit_scale[0]));
+}
+
 }  // namespace
+
+int gating_softmax(const void* logits, int ld, int n, float temperature, const void* logit_scale, void* out, int ldo, int B,
+                   cudaStream_t st) {
+    if (B == 0) return 0;
+    MJV_CHECK(n >= 1 && n <= 32, MJV_ERR_ARG, "gating softmax: 1..32 outputs supported, got %d", n);
+    {
+        LaunchScope scope(TAG_HEAD_FINALIZE, st, 0.0);
+        gating_softmax_kernel<<<(B + 3) / 4, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, n, temperature,
+                                                            static_cast<const __nv_bfloat16*>(logit_scale),
+                                                            static_cast<__nv_bfloat16*>(out), ldo, B);
+    }
+    MJV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 int skinny_linear(const HeadJobs& jobs, int B, cudaStream_t st) {
     const HeadJob* jobs_host = jobs.j;

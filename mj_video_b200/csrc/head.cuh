@@ -43,5 +43,7 @@ struct HeadJobs {  // passed to the kernel by value: no device-side job table to
 
 int skinny_linear(const HeadJobs& jobs, int B, cudaStream_t st);
 int head_finalize(const HeadFinalizeArgs& a, cudaStream_t st);
+int gating_softmax(const void* logits, int ld, int n, float temperature, const void* logit_scale, void* out, int ldo, int B,
+                   cudaStream_t st);
 
 }  // namespace mjv

@@ -193,6 +193,10 @@ class Engine:
             lengths = np.full(B, N, dtype=np.int64)
         if (lengths <= 0).any():
             raise ValueError("empty sequence in batch")
+        if int(lengths.max()) > self.dims.max_pos:
+            # beyond max_position_embeddings the reference re-bases RoPE (dynamic NTK, modeling_internlm2.py:213-221)
+            raise NotImplementedError(f"a row of {int(lengths.max())} tokens exceeds max_position_embeddings="
+                                      f"{self.dims.max_pos}: dynamic-NTK RoPE scaling is not built")
         # last-token index (moe_reward.py:226-228)
         if pad_token_id is None:
             last = np.full(B, N - 1, dtype=np.int64)
@@ -303,6 +307,23 @@ class Engine:
             sb.batch, sb.outputs = b, o
             sb.B, sb.T, sb.M = B, T, M
         return sb
+
+    def gating(self, which: int, x: torch.Tensor, with_softmax: bool = True) -> torch.Tensor:
+        """GatingNetwork as a standalone op (moe_reward.py:16-42): which = 0 aspect_gating, 1 criteria_gating.
+        x [B, llm_hidden] on this device -> [B, n_out] bf16."""
+        if not self._finalized:
+            raise _lib.MjvError("weights not loaded")
+        d = self.dims
+        if x.dim() != 2 or x.shape[1] != d.llm_hidden or x.device != self.device:
+            raise ValueError(f"gating: expected a [B, {d.llm_hidden}] tensor on {self.device}")
+        xb = x.to(torch.bfloat16).contiguous()
+        n_out = d.num_aspects if which == 0 else d.num_objectives
+        out = torch.empty((xb.shape[0], n_out), dtype=torch.bfloat16, device=self.device)
+        with torch.cuda.device(self.device):
+            ws = self.workspace(max(1, xb.shape[0]), 0, 0)
+            _lib.check(self.lib.mjv_gating_forward(self._handle, which, xb.data_ptr(), xb.shape[0], int(with_softmax),
+                                                   out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.current_stream()))
+        return out
 
     def run(self, sb: "StagedBatch") -> dict:
         """Enqueue the whole forward on the current stream (no synchronisation)."""

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import glob
 import os
+import weakref
 from collections import OrderedDict
 from dataclasses import dataclass, fields
 from typing import Optional
@@ -41,11 +42,25 @@ class GatingNetwork(nn.Module):
         layers.append(nn.Linear(in_features, out_features, bias=bias))
         self.layers = nn.ModuleList(layers)
 
-    def forward(self, x):  # pragma: no cover - not a standalone op in this implementation
-        raise NotImplementedError("GatingNetwork is evaluated inside InternVLChatRewardModeling.forward (CUDA head "
-                                  "kernel); there is no standalone / CPU path")
+    def _bind(self, owner, which: int):
+        """Attach to the reward model whose engine holds this network's weights (0 = aspect, 1 = criteria)."""
+        object.__setattr__(self, "_owner", weakref.ref(owner))
+        object.__setattr__(self, "_which", which)
 
-    forward_wo_softmax = forward
+    def _run(self, x, with_softmax: bool):
+        owner = getattr(self, "_owner", lambda: None)()
+        if owner is None:
+            raise RuntimeError("GatingNetwork runs through the engine of its InternVLChatRewardModeling (CUDA head "
+                               "kernels); a free-standing instance has no CPU path")
+        return owner.engine.gating(self._which, x, with_softmax).to(x.dtype)
+
+    def forward(self, x):
+        """softmax(MLP(x) / temperature, dim=1) * logit_scale[0] (moe_reward.py:29-36) — mjv_gating_forward."""
+        return self._run(x, True)
+
+    def forward_wo_softmax(self, x):
+        """The raw logits of the last layer (moe_reward.py:38-42)."""
+        return self._run(x, False)
 
 
 class CustomOutput(OrderedDict):
@@ -129,6 +144,8 @@ class InternVLChatRewardModeling(nn.Module):
                                              temperature=config_dict["gating_temperature"],
                                              hidden_dim=config_dict["gating_hidden_dim"],
                                              n_hidden=config_dict["gating_n_hidden"])
+        self.aspect_gating._bind(self, 0)
+        self.criteria_gating._bind(self, 1)
         self.config = config
         self._engine: Engine | None = None
         self._engine_key = None

@@ -385,3 +385,31 @@ def test_text_only_row_and_surplus_tiles(tiny_engine, gpu):
     _check(mine, ref)
     with pytest.raises(RuntimeError, match="IMG_CONTEXT"):      # fewer embeddings than slots: the reference raises too
         eng.forward(pv[:7], ids1, mask1, synth.PAD, synth.IMG_CONTEXT)
+
+
+def test_gating_network_standalone(gpu):
+    """`GatingNetwork.forward` / `forward_wo_softmax` (moe_reward.py:16-42) as operators of the drop-in
+    module (mjv_gating_forward), against the same MLP in torch with the reference's bf16 rounding points."""
+    from mj_video_b200 import synth
+    from mj_video_b200.model import InternVLChatRewardModeling
+    F = torch.nn.functional
+    d = synth.dims_tiny()
+    sd = synth.make_state_dict(d, seed=21)
+    m = InternVLChatRewardModeling("unused", _tiny_cfg(d))
+    m.load_state_dict(sd, strict=True)
+    m = m.to(torch.bfloat16).cuda().eval()
+    x = (torch.randn(37, d.llm_hidden, generator=torch.Generator().manual_seed(0)) * 2.0).bfloat16().cuda()
+    for name, net, n_out in (("aspect_gating", m.aspect_gating, 5), ("criteria_gating", m.criteria_gating, 28)):
+        h = x
+        for i in range(d.gating_n_hidden + 1):
+            w, b = sd[f"{name}.layers.{i}.weight"].bfloat16().cuda(), sd[f"{name}.layers.{i}.bias"].bfloat16().cuda()
+            h = (h.float() @ w.float().t() + b.float()).bfloat16()
+            if i < d.gating_n_hidden:
+                h = F.relu(h)
+        logits = net.forward_wo_softmax(x)
+        assert logits.shape == (37, n_out) and logits.dtype == torch.bfloat16
+        assert (logits.float() - h.float()).abs().max().item() <= 2.0 ** -7 * max(1.0, h.float().abs().max().item())
+        ref = (F.softmax((h / d.gating_temperature).float(), dim=1).bfloat16() * sd[f"{name}.logit_scale"].bfloat16().cuda())
+        got = net(x)
+        assert (got.float() - ref.float()).abs().max().item() <= 2e-2
+        assert torch.allclose(got.float().sum(1), torch.ones(37, device="cuda"), atol=2e-2)

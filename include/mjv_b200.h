@@ -217,6 +217,8 @@ typedef struct mjv_batch {
     const int32_t* work_last;  /* device [2*n_work_last]: the (sequence, query block) items that contain a gathered
                                   row — the only attention blocks the LAST decoder layer needs (NULL = all)    */
     int32_t n_work_last;
+    int32_t max_seq_len;       /* longest sequence of the batch: must not exceed the rows of the loaded RoPE tables
+                                  (max_position_embeddings, or more after the host re-based them: dynamic NTK)   */
 } mjv_batch;
 
 typedef struct mjv_outputs {

@@ -70,7 +70,7 @@ class Batch(C.Structure):
         ("pixel_values", C.c_void_p), ("pixel_dtype", C.c_int32),
         ("token_ids", C.c_void_p), ("row_pos", C.c_void_p), ("row_vt", C.c_void_p), ("img_rows", C.c_void_p),
         ("cu_seqlens", C.c_void_p), ("vt_starts", C.c_void_p), ("work", C.c_void_p), ("gather_rows", C.c_void_p),
-        ("work_last", C.c_void_p), ("n_work_last", C.c_int32),
+        ("work_last", C.c_void_p), ("n_work_last", C.c_int32), ("max_seq_len", C.c_int32),
     ]
 
 

@@ -54,6 +54,7 @@ struct mjv_handle {
     std::vector<mjv::LlmLayerW> llm;
     const void* final_norm = nullptr;
     const float *rope_cos = nullptr, *rope_sin = nullptr;
+    long long rope_rows = 0;
     const void *regression = nullptr, *transform = nullptr;
     mjv::GateW aspect, criteria;
     int *group_offsets_dev = nullptr, *group_items_dev = nullptr;
@@ -177,6 +178,13 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
     // rope tables stay fp32
     if (key == "rope.cos" || key == "rope.sin") {
         MJV_CHECK(dtype == MJV_DTYPE_F32, MJV_ERR_ARG, "%s must be float32", key.c_str());
+        // the table may be re-loaded with more rows (dynamic-NTK re-basing for a batch longer than max_pos): replace it
+        auto old = h->weights.find(key);
+        if (old != h->weights.end() && (old->second.rows != rows || old->second.cols != cols)) {
+            MJV_CUDA_OK(cudaDeviceSynchronize());  // launches that still read the old table
+            cudaFree(old->second.ptr);
+            h->weights.erase(old);
+        }
         Tensor* t;
         MJV_PROPAGATE(ensure_tensor(h, key, rows, cols, cols, true, &t));
         MJV_CUDA_OK(cudaMemcpy(t->ptr, data, n_elem * 4, cudaMemcpyDefault));
@@ -330,10 +338,17 @@ int finalize(mjv_handle* h) {
     MJV_PROPAGATE(need(h, lm + "norm.weight", &h->final_norm));
     const void* tmp;
     // [max_pos, 64]: one column per rotary pair of the 128-wide head slot (pad pairs: cos 1, sin 0)
-    MJV_PROPAGATE(need(h, "rope.cos", &tmp, static_cast<long long>(c.max_pos) * (kHeadSlot / 2)));
+    // (rows >= max_pos: the host re-loads a longer, re-based table when a batch exceeds max_position_embeddings)
+    MJV_PROPAGATE(need(h, "rope.cos", &tmp));
     h->rope_cos = static_cast<const float*>(tmp);
-    MJV_PROPAGATE(need(h, "rope.sin", &tmp, static_cast<long long>(c.max_pos) * (kHeadSlot / 2)));
+    MJV_PROPAGATE(need(h, "rope.sin", &tmp));
     h->rope_sin = static_cast<const float*>(tmp);
+    {
+        const Tensor &tc = h->weights.at("rope.cos"), &ts = h->weights.at("rope.sin");
+        MJV_CHECK(tc.cols == kHeadSlot / 2 && ts.cols == kHeadSlot / 2 && tc.rows == ts.rows && tc.rows >= c.max_pos,
+                  MJV_ERR_STATE, "rope tables must be [>= %d, %d] float32", c.max_pos, kHeadSlot / 2);
+        h->rope_rows = tc.rows;
+    }
     MJV_PROPAGATE(need(h, "regression_layer.weight", &h->regression));
     MJV_PROPAGATE(need(h, "reward_transform_matrix", &h->transform));
     for (int net = 0; net < 2; ++net) {
@@ -544,6 +559,8 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
     MJV_CHECK(d.hd % 2 == 0 && d.hd >= 2 && d.hd <= d.hs, MJV_ERR_ARG, "LLM head_dim %d unsupported (even, <= 128)", d.hd);
     const long long M = b.n_tokens;
     MJV_CHECK(M > 0 && M < (1LL << 31) / 16, MJV_ERR_ARG, "bad token count %lld", M);
+    MJV_CHECK(b.max_seq_len > 0 && b.max_seq_len <= h->rope_rows, MJV_ERR_ARG,
+              "longest sequence (%d tokens) exceeds the loaded RoPE table (%lld rows)", b.max_seq_len, h->rope_rows);
     const int nq = d.Hq * d.hs, nk = d.Hkv * d.hs;
     __nv_bfloat16* hcur = static_cast<__nv_bfloat16*>(embeds);
     MJV_ALLOC(xn, __nv_bfloat16*, ar, static_cast<size_t>(M) * d.D * 2);

@@ -65,6 +65,7 @@ class EngineDims:
     aspect2criteria: dict
     downsample_ratio: float = 0.5
     mlp1_eps: float = 1e-5
+    rope_scaling_factor: float | None = 2.0   # InternLM2 rope_scaling {'type': 'dynamic', 'factor': f}; None = no scaling
 
     @staticmethod
     def from_synth(d) -> "EngineDims":
@@ -77,7 +78,8 @@ class EngineDims:
             vocab=d.vocab, rms_eps=d.rms_eps, rope_theta=d.rope_theta, max_pos=d.max_pos,
             num_objectives=d.num_objectives, num_aspects=d.num_aspects, gating_hidden=d.gating_hidden,
             gating_n_hidden=d.gating_n_hidden, gating_temperature=d.gating_temperature,
-            aspect2criteria={k: list(v) for k, v in d.aspect2criteria.items()}, downsample_ratio=d.downsample_ratio)
+            aspect2criteria={k: list(v) for k, v in d.aspect2criteria.items()}, downsample_ratio=d.downsample_ratio,
+            rope_scaling_factor=getattr(d, "rope_scaling_factor", 2.0))
 
     @property
     def vit_seq(self) -> int:
@@ -133,28 +135,49 @@ class Engine:
             pass
 
     # -------------------------------------------------------------------------------------------- weights
-    def _load_rope(self):
+    def _load_rope(self, seq_len: int | None = None):
         """cos/sin tables as the reference's rotary modules produce them in a bf16 model, one column per rotary pair of
         the 128-wide head slot the kernels use (pairs beyond head_dim/2 are padding: cos 1, sin 0).
-        InternLM2 (modeling_internlm2.py:147-170): fp32 tables built at init, cast with the model -> bf16-rounded values.
-        Llama branch (modeling_internvl_chat.py:125-126 -> transformers LlamaRotaryEmbedding): `inv_freq` is a buffer,
-        so `model.to(bfloat16)` rounds inv_freq itself to bf16; angles are then computed in fp32 and cos/sin cast to
-        bf16. `rope_inv_freq_bf16=False` keeps fp32 inv_freq (a bf16 checkpoint loaded without a later `.to()`)."""
+        InternLM2 (modeling_internlm2.py:147-180): fp32 tables for max_position_embeddings rows built at init, cast with
+        the model -> bf16-rounded values. When a padded batch is LONGER than the cached table, the dynamic-NTK class
+        (:210-231) re-bases theta for that length (only beyond max_position_embeddings), rebuilds the table and keeps it
+        for every later call — `seq_len` does the same here.
+        Llama branch (modeling_internvl_chat.py:125-126 -> transformers LlamaRotaryEmbedding): no cache and no scaling;
+        `inv_freq` is a buffer, so `model.to(bfloat16)` rounds inv_freq itself to bf16; angles are then computed in fp32
+        and cos/sin cast to bf16. `rope_inv_freq_bf16=False` keeps fp32 inv_freq (a bf16 checkpoint loaded without a
+        later `.to()`)."""
         d = self.dims
         hd = d.llm_hidden // d.llm_heads
         if hd % 2 or hd > 128:
             raise _lib.MjvError(f"LLM head_dim {hd} unsupported (even, <= 128)")
-        inv_freq = 1.0 / (d.rope_theta ** (torch.arange(0, hd, 2).float() / hd))
+        rows = d.max_pos if seq_len is None else int(seq_len)
+        base = d.rope_theta
+        if d.llm_arch == 0 and seq_len is not None:
+            if d.rope_scaling_factor is None:
+                # the plain InternLM2RotaryEmbedding re-caches with the model's (bf16) inv_freq and bf16 positions
+                raise NotImplementedError(f"a batch of {rows} positions exceeds max_position_embeddings={d.max_pos} and "
+                                          "the config has no dynamic rope_scaling")
+            if rows > d.max_pos:
+                f = d.rope_scaling_factor
+                base = base * ((f * rows / d.max_pos) - (f - 1)) ** (hd / (hd - 2))
+        inv_freq = 1.0 / (base ** (torch.arange(0, hd, 2).float() / hd))
         if d.llm_arch == 1 and self.rope_inv_freq_bf16:
             inv_freq = inv_freq.to(torch.bfloat16).float()
-        t = torch.arange(d.max_pos, dtype=inv_freq.dtype)
+        t = torch.arange(rows, dtype=inv_freq.dtype)
         freqs = torch.einsum("i,j->ij", t, inv_freq)
-        cos = torch.ones((d.max_pos, 64), dtype=torch.float32)
-        sin = torch.zeros((d.max_pos, 64), dtype=torch.float32)
+        cos = torch.ones((rows, 64), dtype=torch.float32)
+        sin = torch.zeros((rows, 64), dtype=torch.float32)
         cos[:, : hd // 2] = freqs.cos().to(torch.bfloat16).to(torch.float32)
         sin[:, : hd // 2] = freqs.sin().to(torch.bfloat16).to(torch.float32)
         self.load_weight("rope.cos", cos)
         self.load_weight("rope.sin", sin)
+        self._rope_rows = rows
+
+    def _ensure_rope(self, padded_len: int):
+        """The reference looks at kv_seq_len = the PADDED batch length (modeling_internlm2.py:172-175, 380)."""
+        if padded_len > self._rope_rows:
+            self._load_rope(seq_len=padded_len)
+            self.finalize()
 
     def load_weight(self, key: str, tensor: torch.Tensor):
         t = tensor.detach()
@@ -193,10 +216,6 @@ class Engine:
             lengths = np.full(B, N, dtype=np.int64)
         if (lengths <= 0).any():
             raise ValueError("empty sequence in batch")
-        if int(lengths.max()) > self.dims.max_pos:
-            # beyond max_position_embeddings the reference re-bases RoPE (dynamic NTK, modeling_internlm2.py:213-221)
-            raise NotImplementedError(f"a row of {int(lengths.max())} tokens exceeds max_position_embeddings="
-                                      f"{self.dims.max_pos}: dynamic-NTK RoPE scaling is not built")
         # last-token index (moe_reward.py:226-228)
         if pad_token_id is None:
             last = np.full(B, N - 1, dtype=np.int64)
@@ -269,6 +288,7 @@ class Engine:
         object can be launched any number of times with `run` (its inputs then already live in HBM)."""
         if not self._finalized:
             self.finalize()
+        self._ensure_rope(int(input_ids.shape[1]))
         d = self.dims
         if pixel_values.dim() != 4:
             raise ValueError(f"wrong pixel_values size: {tuple(pixel_values.shape)}")  # modeling_intern_vit.py:410-413
@@ -301,6 +321,7 @@ class Engine:
                       "work_last"):
                 setattr(b, k, base + 4 * off[k])
             b.n_work_last = info["n_work_last"]
+            b.max_seq_len = int(info["lengths"].max())
             o = _lib.Outputs()
             o.scores, o.extras = sb.scores.data_ptr(), sb.extras.data_ptr()
             o.hidden_state, o.prompt_embedding = sb.hidden.data_ptr(), sb.prompt.data_ptr()

@@ -111,7 +111,8 @@ def _engine_dims(config) -> EngineDims:
         gating_hidden=config.gating_hidden_dim, gating_n_hidden=config.gating_n_hidden,
         gating_temperature=config.gating_temperature,
         aspect2criteria={k: list(v) for k, v in config.aspect2criteria.items()},
-        downsample_ratio=config.downsample_ratio)
+        downsample_ratio=config.downsample_ratio,
+        rope_scaling_factor=(rs or {}).get("factor") if arch == "InternLM2ForCausalLM" else None)
 
 
 class InternVLChatRewardModeling(nn.Module):

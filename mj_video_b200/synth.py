@@ -49,6 +49,7 @@ class ModelDims:
     rms_eps: float = 1e-5
     rope_theta: float = 1000000.0
     max_pos: int = 32768
+    rope_scaling_factor: float | None = 2.0   # rope_scaling {'type': 'dynamic', 'factor': 2.0} (InternLM2 branch only)
     # projector
     downsample_ratio: float = 0.5
     # head (eval_genai_mjvideo.py:36-47)

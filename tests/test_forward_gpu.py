@@ -413,3 +413,40 @@ def test_gating_network_standalone(gpu):
         got = net(x)
         assert (got.float() - ref.float()).abs().max().item() <= 2e-2
         assert torch.allclose(got.float().sum(1), torch.ones(37, device="cuda"), atol=2e-2)
+
+
+def test_dynamic_ntk_rope_beyond_max_positions(gpu):
+    """A padded batch longer than max_position_embeddings: the reference's dynamic-NTK rotary class re-bases theta for that
+    length and KEEPS the re-based table for later, shorter calls (modeling_internlm2.py:172-175, 210-231; the oracle's
+    restatement of it is pinned bit-exact to the reference in test_oracle_vs_reference.py). Same sequence of calls here."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from mj_video_b200.engine import Engine, EngineDims
+    from oracle import port
+    d = synth.dims_tiny()
+    d.max_pos = 1024
+    sd = synth.make_state_dict(d, seed=8, include_lm_head=False)
+    eng = Engine(EngineDims.from_synth(d), gpu)
+    eng.load_state_dict(sd)
+    orc = port.Oracle(d, sd, dtype=torch.float32, device=gpu)
+    pv = load_video(synth.make_video(31), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)[0]
+    long_ids, long_mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=40)])      # 2181 tokens > 1024
+    short_ids, short_mask = synth.pad_batch([synth.make_input_ids(1, [1] * 2, n_cap=20)])     # 599 tokens
+    first = None
+    for step, (ids, mask, px) in enumerate(((short_ids, short_mask, pv[:2]), (long_ids, long_mask, pv),
+                                            (short_ids, short_mask, pv[:2]))):
+        mine = _as_dict(d, eng.forward(px, ids, mask, synth.PAD, synth.IMG_CONTEXT))
+        ref = orc.forward(px.float(), ids, mask)
+        _check(mine, ref)
+        if step == 0:
+            first = mine["rewards"].clone()
+    assert eng._rope_rows == long_ids.shape[1] == orc.rope_cached
+    # the short prompt scores differently once the table has been re-based (the reference's cache is stateful)
+    assert not torch.equal(first, mine["rewards"])
+    # without dynamic scaling in the config there is nothing to re-base with: refuse instead of indexing out of bounds
+    d2 = synth.dims_tiny()
+    d2.max_pos, d2.rope_scaling_factor = 1024, None
+    eng2 = Engine(EngineDims.from_synth(d2), gpu)
+    eng2.load_state_dict(sd)
+    with pytest.raises(NotImplementedError, match="max_position_embeddings"):
+        eng2.forward(pv, long_ids, long_mask, synth.PAD, synth.IMG_CONTEXT)

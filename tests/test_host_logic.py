@@ -75,16 +75,6 @@ def test_prepare_batch_errors():
     assert info["n_img"] == 16 * 256
 
 
-def test_rows_longer_than_the_rope_table_are_refused():
-    """Beyond max_position_embeddings the reference switches to dynamic-NTK RoPE (modeling_internlm2.py:213-221), which
-    is not built: the engine must refuse instead of indexing past its cos/sin tables."""
-    e = _engine_stub()
-    e.dims.max_pos = 2048
-    ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=40)])   # 2181 tokens
-    with pytest.raises(NotImplementedError, match="max_position_embeddings"):
-        e.prepare_batch(ids, mask, 8, synth.PAD, synth.IMG_CONTEXT)
-
-
 def test_single_row_without_pad_token():
     e = _engine_stub()
     rows = [synth.make_input_ids(0, [1] * 8, n_cap=20)]

@@ -75,6 +75,26 @@ def test_text_only_row_and_surplus_tiles(ref_model, capsys):
         assert torch.equal(ref[k].float(), out[k].float()), k
 
 
+def test_dynamic_ntk_rope_beyond_max_positions():
+    """A padded batch longer than max_position_embeddings makes InternLM2DynamicNTKScalingRotaryEmbedding re-base theta
+    for that length and keep the re-based cache for later (shorter) calls (modeling_internlm2.py:172-175, 210-231)."""
+    from oracle import reference_harness as rh
+    d = synth.dims_tiny()
+    d.max_pos = 1024
+    sd = synth.make_state_dict(d, seed=8)
+    m = rh.build_reference_model(d, sd)
+    orc = port.Oracle(d, sd)
+    pv = rh.reference_load_video(synth.make_video(31), num_segments=8, max_num=1)[0]
+    long_ids, long_mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=40)])          # 2181 tokens > 1024
+    short_ids, short_mask = synth.pad_batch([synth.make_input_ids(1, [1] * 2, n_cap=20)])         # 599 tokens
+    for ids, mask, px in ((short_ids, short_mask, pv[:2]), (long_ids, long_mask, pv), (short_ids, short_mask, pv[:2])):
+        ref = rh.reference_forward(m, px, ids, mask)
+        out = orc.forward(px, ids, mask)
+        for k in ref:
+            assert torch.equal(ref[k].float(), out[k].float()), (k, ids.shape)
+    assert orc.rope_cached == long_ids.shape[1]
+
+
 def test_reference_errors(ref_model):
     d, sd, m, rh = ref_model
     pv = torch.zeros(8, 3, 448, 448)

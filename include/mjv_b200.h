@@ -127,7 +127,8 @@ int mjv_attention(const mjv_attn_desc* desc, void* stream);
 /* ------------------------------------------------------------------------------------------------------------
  * Row-wise primitives (test hooks; the engine calls the same kernels internally)
  *   mjv_layernorm               nn.LayerNorm            modeling_intern_vit.py:291,293
- *   mjv_pixel_shuffle_layernorm pixel_shuffle('v2') + mlp1[0]  modeling_internvl_chat.py:228-262,136
+ *   mjv_pixel_shuffle_layernorm pixel_shuffle + mlp1[0]  modeling_internvl_chat.py:228-262,136 (ps_v1 != 0: ps_version
+ *                               'v1', the transposed token grid the reference produces when it skips the final permute)
  *   mjv_rmsnorm                 InternLM2RMSNorm        modeling_internlm2.py:138-143 (row_idx gathers source rows)
  *   mjv_embed_tokens            tok_embeddings lookup   modeling_internvl_chat.py:163 (IMG_CONTEXT rows skipped)
  *   mjv_im2col_patches          nn.Conv2d(3,C,14,14) operand layout  modeling_intern_vit.py:164
@@ -135,7 +136,7 @@ int mjv_attention(const mjv_attn_desc* desc, void* stream);
 int mjv_layernorm(const void* x, const void* w, const void* b, void* out, int64_t rows, int32_t C, float eps,
                   void* stream);
 int mjv_pixel_shuffle_layernorm(const void* vit_hidden, const void* w, const void* b, void* out, int32_t tiles,
-                                int32_t seq, int32_t c_vit, float eps, void* stream);
+                                int32_t seq, int32_t c_vit, float eps, int32_t ps_v1, void* stream);
 int mjv_rmsnorm(const void* x, const void* w, void* out, int64_t rows, int32_t C, float eps, const int32_t* row_idx,
                 void* stream);
 int mjv_embed_tokens(const int32_t* ids, const void* table, void* out, int64_t rows, int32_t C, int32_t img_ctx_id,
@@ -168,7 +169,7 @@ enum { MJV_LLM_INTERNLM2 = 0, MJV_LLM_LLAMA = 1 };
 
 typedef struct mjv_config {
     int32_t image_size, patch_size;
-    int32_t vit_hidden, vit_heads, vit_mlp, vit_layers;
+    int32_t vit_hidden, vit_heads, vit_mlp, vit_layers; /* vit_layers: encoder layers actually APPLIED (select_layer) */
     float vit_eps;
     int32_t llm_arch;
     int32_t llm_hidden, llm_inter, llm_layers, llm_heads, llm_kv_heads, vocab;
@@ -179,6 +180,7 @@ typedef struct mjv_config {
     float gating_temperature;
     int32_t group_offsets[33]; /* aspect2criteria in dict order: items of aspect a are                      */
     int32_t group_items[32];   /*   group_items[group_offsets[a] .. group_offsets[a+1])                     */
+    int32_t ps_version;        /* pixel-shuffle layout: 0 or 2 = 'v2', 1 = 'v1' (modeling_internvl_chat.py:237-241)   */
 } mjv_config;
 
 int mjv_create(const mjv_config* cfg, mjv_handle** out);

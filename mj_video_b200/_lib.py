@@ -59,6 +59,7 @@ class Config(C.Structure):
         ("num_objectives", C.c_int32), ("num_aspects", C.c_int32), ("gating_hidden", C.c_int32),
         ("gating_n_hidden", C.c_int32), ("gating_temperature", C.c_float),
         ("group_offsets", C.c_int32 * 33), ("group_items", C.c_int32 * 32),
+        ("ps_version", C.c_int32),
     ]
 
 
@@ -110,7 +111,7 @@ def load() -> C.CDLL:
     lib.mjv_attention.restype = C.c_int
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     lib.mjv_layernorm.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp]
-    lib.mjv_pixel_shuffle_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp]
+    lib.mjv_pixel_shuffle_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp]
     lib.mjv_rmsnorm.argtypes = [vp, vp, vp, i64, i32, f32, vp, vp]
     lib.mjv_embed_tokens.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
     lib.mjv_im2col_patches.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp]

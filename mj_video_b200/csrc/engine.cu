@@ -536,7 +536,7 @@ int project_and_splice(mjv_handle* h, const void* vit_hidden, const mjv_batch& b
     if (T == 0 || b.n_img_tokens == 0) return 0;
     MJV_ALLOC(pn, __nv_bfloat16*, ar, static_cast<size_t>(Mp) * 4 * d.C * 2);
     MJV_ALLOC(p1, __nv_bfloat16*, ar, static_cast<size_t>(Mp) * d.D * 2);
-    MJV_PROPAGATE(pixel_shuffle_layernorm(vit_hidden, h->mlp1_ln_w, h->mlp1_ln_b, pn, T, d.S, d.C, c.mlp1_eps, st));
+    MJV_PROPAGATE(pixel_shuffle_layernorm(vit_hidden, h->mlp1_ln_w, h->mlp1_ln_b, pn, T, d.S, d.C, c.mlp1_eps, c.ps_version == 1, st));
     {
         mjv_gemm_desc g = gemm_base(pn, 4 * d.C, h->mlp1_1_w, 4 * d.C, p1, d.D, (int)Mp, d.D, 4 * d.C, MJV_EPI_GELU);
         g.bias = h->mlp1_1_b;

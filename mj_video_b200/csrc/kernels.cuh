@@ -10,7 +10,7 @@ int gemm_bf16(const mjv_gemm_desc& d, cudaStream_t stream);
 int attention(const mjv_attn_desc& d, cudaStream_t stream);
 int layernorm(const void* x, const void* w, const void* b, void* out, long long rows, int C, float eps, cudaStream_t st);
 int pixel_shuffle_layernorm(const void* vit_hidden, const void* w, const void* b, void* out, int tiles, int seq,
-                            int c_vit, float eps, cudaStream_t st);
+                            int c_vit, float eps, int ps_v1, cudaStream_t st);
 int rmsnorm(const void* x, const void* w, void* out, long long rows, int C, float eps, const int* row_idx,
             cudaStream_t st);
 int embed_tokens(const int* ids, const void* table, void* out, long long rows, int C, int img_ctx_id, int vocab,

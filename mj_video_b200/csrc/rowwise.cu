@@ -67,9 +67,15 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
         const int per_tile = half * half;
         const long long t = row / per_tile;
         const int ij = static_cast<int>(row - t * per_tile);
-        const int i = ij / half, j = ij - i * half;
+        int i = ij / half, j = ij - i * half;
+        if (seq < 0) {  // ps_version 'v1': the output grid is the transpose of 'v2' (no final permute in the reference)
+            const int tmp = i;
+            i = j;
+            j = tmp;
+        }
         cq = C / 4;
-        g_base = t * seq + 1 + static_cast<long long>(2 * i) * grid_g + 2 * j;
+        const int seq_abs = seq < 0 ? -seq : seq;
+        g_base = t * seq_abs + 1 + static_cast<long long>(2 * i) * grid_g + 2 * j;
     }
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
@@ -293,7 +299,7 @@ int layernorm(const void* x, const void* w, const void* b, void* out, long long 
 }
 
 int pixel_shuffle_layernorm(const void* vit_hidden, const void* w, const void* b, void* out, int tiles, int seq,
-                            int c_vit, float eps, cudaStream_t st) {
+                            int c_vit, float eps, int ps_v1, cudaStream_t st) {
     if (tiles == 0) return 0;
     int g = 1;
     while (g * g < seq - 1) ++g;
@@ -301,7 +307,7 @@ int pixel_shuffle_layernorm(const void* vit_hidden, const void* w, const void* b
     MJV_CHECK((c_vit % 8) == 0, MJV_ERR_ARG, "pixel_shuffle: channels %d", c_vit);
     const long long rows = static_cast<long long>(tiles) * (g / 2) * (g / 2);
     return launch_ln<true>((const __nv_bfloat16*)vit_hidden, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b,
-                           (__nv_bfloat16*)out, rows, 4 * c_vit, eps, c_vit, g, seq, st);
+                           (__nv_bfloat16*)out, rows, 4 * c_vit, eps, c_vit, g, ps_v1 ? -seq : seq, st);
 }
 
 int rmsnorm(const void* x, const void* w, void* out, long long rows, int C, float eps, const int* row_idx,
@@ -399,8 +405,9 @@ extern "C" int mjv_layernorm(const void* x, const void* w, const void* b, void* 
     return mjv::layernorm(x, w, b, out, rows, C, eps, static_cast<cudaStream_t>(stream));
 }
 extern "C" int mjv_pixel_shuffle_layernorm(const void* vit_hidden, const void* w, const void* b, void* out,
-                                           int32_t tiles, int32_t seq, int32_t c_vit, float eps, void* stream) {
-    return mjv::pixel_shuffle_layernorm(vit_hidden, w, b, out, tiles, seq, c_vit, eps,
+                                           int32_t tiles, int32_t seq, int32_t c_vit, float eps, int32_t ps_v1,
+                                           void* stream) {
+    return mjv::pixel_shuffle_layernorm(vit_hidden, w, b, out, tiles, seq, c_vit, eps, ps_v1,
                                         static_cast<cudaStream_t>(stream));
 }
 extern "C" int mjv_rmsnorm(const void* x, const void* w, void* out, int64_t rows, int32_t C, float eps,

@@ -66,20 +66,22 @@ class EngineDims:
     downsample_ratio: float = 0.5
     mlp1_eps: float = 1e-5
     rope_scaling_factor: float | None = 2.0   # InternLM2 rope_scaling {'type': 'dynamic', 'factor': f}; None = no scaling
+    ps_version: int = 2                        # 1 = 'v1' pixel-shuffle layout (transposed token grid)
 
     @staticmethod
     def from_synth(d) -> "EngineDims":
         """From mj_video_b200.synth.ModelDims."""
         return EngineDims(
             image_size=d.image_size, patch_size=d.patch_size, vit_hidden=d.vit_hidden, vit_heads=d.vit_heads,
-            vit_mlp=d.vit_mlp, vit_layers=d.vit_layers, vit_eps=d.vit_eps,
+            vit_mlp=d.vit_mlp, vit_layers=applied_vit_layers(d.vit_layers, getattr(d, "select_layer", -1)), vit_eps=d.vit_eps,
             llm_arch=1 if getattr(d, "llm_arch", "") == "LlamaForCausalLM" else 0, llm_hidden=d.llm_hidden,
             llm_inter=d.llm_inter, llm_layers=d.llm_layers, llm_heads=d.llm_heads, llm_kv_heads=d.llm_kv_heads,
             vocab=d.vocab, rms_eps=d.rms_eps, rope_theta=d.rope_theta, max_pos=d.max_pos,
             num_objectives=d.num_objectives, num_aspects=d.num_aspects, gating_hidden=d.gating_hidden,
             gating_n_hidden=d.gating_n_hidden, gating_temperature=d.gating_temperature,
             aspect2criteria={k: list(v) for k, v in d.aspect2criteria.items()}, downsample_ratio=d.downsample_ratio,
-            rope_scaling_factor=getattr(d, "rope_scaling_factor", 2.0))
+            rope_scaling_factor=getattr(d, "rope_scaling_factor", 2.0),
+            ps_version=1 if getattr(d, "ps_version", "v2") == "v1" else 2)
 
     @property
     def vit_seq(self) -> int:
@@ -88,6 +90,17 @@ class EngineDims:
     @property
     def tokens_per_tile(self) -> int:
         return int((self.image_size // self.patch_size) ** 2 * self.downsample_ratio ** 2)
+
+
+def applied_vit_layers(n_layers: int, select_layer: int) -> int:
+    """Encoder layers that produce the hidden state `extract_feature` reads (modeling_internvl_chat.py:244-254):
+    select_layer == -1 -> last_hidden_state (all layers); else hidden_states[select_layer] of the n_layers + 1 states."""
+    if select_layer == -1:
+        return n_layers
+    k = n_layers + 1 + select_layer if select_layer < 0 else select_layer
+    if not 0 < k <= n_layers:
+        raise ValueError(f"select_layer={select_layer} is outside the {n_layers}-layer vision encoder")
+    return k
 
 
 _DTYPES = {torch.float32: _lib.MJV_DTYPE_F32, torch.bfloat16: _lib.MJV_DTYPE_BF16, torch.float16: _lib.MJV_DTYPE_F16}
@@ -109,7 +122,7 @@ class Engine:
         for f in ("image_size", "patch_size", "vit_hidden", "vit_heads", "vit_mlp", "vit_layers", "vit_eps", "llm_arch",
                   "llm_hidden", "llm_inter", "llm_layers", "llm_heads", "llm_kv_heads", "vocab", "rms_eps", "max_pos",
                   "mlp1_eps", "num_objectives", "num_aspects", "gating_hidden", "gating_n_hidden",
-                  "gating_temperature"):
+                  "gating_temperature", "ps_version"):
             setattr(cfg, f, getattr(dims, f))
         off = 0
         for a, (_, items) in enumerate(dims.aspect2criteria.items()):

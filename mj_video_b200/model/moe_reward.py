@@ -20,7 +20,7 @@ from typing import Optional
 import torch
 from torch import nn
 
-from ..engine import Engine, EngineDims, find_token_for_gating  # noqa: F401  (re-exported like the reference)
+from ..engine import Engine, EngineDims, applied_vit_layers, find_token_for_gating  # noqa: F401  (re-exported like the reference)
 from .internvl2 import InternVLChatModel, InternVLChatRewardModelingConfig  # noqa: F401
 
 token_pattern = [92542, 92543, 525, 11353, 364]  # moe_reward.py:48
@@ -96,14 +96,14 @@ def _engine_dims(config) -> EngineDims:
         raise NotImplementedError(f"{arch} is not implemented.")  # modeling_internvl_chat.py:125-130
     if vc.qk_normalization or vc.norm_type != "layer_norm" or not vc.qkv_bias:
         raise NotImplementedError("only the InternViT-300M flavour (layer_norm, qkv_bias, no qk_normalization) is built")
-    if config.ps_version != "v2" or config.select_layer != -1:
-        raise NotImplementedError("only ps_version='v2' and select_layer=-1 are built")
+    if config.ps_version not in ("v1", "v2"):
+        raise NotImplementedError(f"ps_version {config.ps_version!r} is unknown")
     rs = lc.rope_scaling
     if rs is not None and rs.get("type") not in ("dynamic",):
         raise NotImplementedError(f"rope_scaling {rs} is not built")
     return EngineDims(
         image_size=config.force_image_size or vc.image_size, patch_size=vc.patch_size, vit_hidden=vc.hidden_size,
-        vit_heads=vc.num_attention_heads, vit_mlp=vc.intermediate_size, vit_layers=vc.num_hidden_layers,
+        vit_heads=vc.num_attention_heads, vit_mlp=vc.intermediate_size, vit_layers=applied_vit_layers(vc.num_hidden_layers, config.select_layer),
         vit_eps=vc.layer_norm_eps, llm_arch=0 if arch == "InternLM2ForCausalLM" else 1, llm_hidden=lc.hidden_size,
         llm_inter=lc.intermediate_size, llm_layers=lc.num_hidden_layers, llm_heads=lc.num_attention_heads,
         llm_kv_heads=lc.num_key_value_heads, vocab=lc.vocab_size, rms_eps=lc.rms_norm_eps, rope_theta=lc.rope_theta,
@@ -112,7 +112,8 @@ def _engine_dims(config) -> EngineDims:
         gating_temperature=config.gating_temperature,
         aspect2criteria={k: list(v) for k, v in config.aspect2criteria.items()},
         downsample_ratio=config.downsample_ratio,
-        rope_scaling_factor=(rs or {}).get("factor") if arch == "InternLM2ForCausalLM" else None)
+        rope_scaling_factor=(rs or {}).get("factor") if arch == "InternLM2ForCausalLM" else None,
+        ps_version=1 if config.ps_version == "v1" else 2)
 
 
 class InternVLChatRewardModeling(nn.Module):

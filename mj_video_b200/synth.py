@@ -52,6 +52,8 @@ class ModelDims:
     rope_scaling_factor: float | None = 2.0   # rope_scaling {'type': 'dynamic', 'factor': 2.0} (InternLM2 branch only)
     # projector
     downsample_ratio: float = 0.5
+    select_layer: int = -1        # ViT hidden state fed to the projector (modeling_internvl_chat.py:244-254)
+    ps_version: str = "v2"        # pixel-shuffle layout (modeling_internvl_chat.py:237-241)
     # head (eval_genai_mjvideo.py:36-47)
     num_objectives: int = 28
     num_aspects: int = 5

@@ -90,7 +90,7 @@ def build_reference_config(d):
         llm.update(bias=False, rope_scaling=None if f is None else {"type": "dynamic", "factor": f})
     cfg = moe_reward.InternVLChatRewardModelingConfig(
         vision_config=vision, llm_config=llm, template=getattr(d, "template", "internlm2-chat"), downsample_ratio=d.downsample_ratio,
-        ps_version="v2", select_layer=-1, force_image_size=d.image_size, num_objectives=d.num_objectives,
+        ps_version=getattr(d, "ps_version", "v2"), select_layer=getattr(d, "select_layer", -1), force_image_size=d.image_size, num_objectives=d.num_objectives,
         num_aspects=d.num_aspects, aspect2criteria={k: list(v) for k, v in d.aspect2criteria.items()},
         gating_temperature=d.gating_temperature, gating_hidden_dim=d.gating_hidden, gating_n_hidden=d.gating_n_hidden)
     return cfg

@@ -450,3 +450,27 @@ def test_dynamic_ntk_rope_beyond_max_positions(gpu):
     eng2.load_state_dict(sd)
     with pytest.raises(NotImplementedError, match="max_position_embeddings"):
         eng2.forward(pv, long_ids, long_mask, synth.PAD, synth.IMG_CONTEXT)
+
+
+def test_select_layer_and_ps_version_v1(gpu):
+    """hidden_states[select_layer] of the ViT (only the layers that produce it are run) and the 'v1' pixel-shuffle layout,
+    against the oracle (itself pinned bit-exact to the reference for this configuration)."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from mj_video_b200.engine import Engine, EngineDims
+    from oracle import port
+    d = synth.dims_tiny()
+    d.vit_layers, d.select_layer, d.ps_version = 3, -2, "v1"
+    sd = synth.make_state_dict(d, seed=9, include_lm_head=False)
+    ed = EngineDims.from_synth(d)
+    assert ed.vit_layers == 2 and ed.ps_version == 1
+    eng = Engine(ed, gpu)
+    eng.load_state_dict(sd)       # the unused third ViT layer is accepted and ignored
+    pv = load_video(synth.make_video(33), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)[0]
+    ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=25)])
+    mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
+    ref = port.Oracle(d, sd, dtype=torch.float32, device=gpu).forward(pv.float(), ids, mask)
+    _check(mine, ref)
+    d.ps_version = "v2"
+    other = port.Oracle(d, sd, dtype=torch.float32, device=gpu).forward(pv.float(), ids, mask)
+    assert (other["rewards"].float() - ref["rewards"].float()).abs().max().item() > 1e-3   # the layouts really differ

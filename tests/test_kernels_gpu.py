@@ -240,11 +240,14 @@ def test_rowwise_kernels(ops, built_lib):
     w = torch.randn(4 * Cv, device="cuda", generator=g).bfloat16()
     b = torch.randn(4 * Cv, device="cuda", generator=g).bfloat16()
     out = torch.empty(T * 256, 4 * Cv, device="cuda", dtype=torch.bfloat16)
-    _lib.check(lib.mjv_pixel_shuffle_layernorm(hid.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), T, S, Cv,
-                                               1e-5, st))
-    orc = port.Oracle.__new__(port.Oracle)
-    ps = orc.pixel_shuffle(hid[:, 1:].float().reshape(T, 32, 32, Cv), 0.5).reshape(T * 256, 4 * Cv)
-    close(out, torch.nn.functional.layer_norm(ps, (4 * Cv,), w.float(), b.float(), 1e-5).bfloat16(), ulps=1.5)
+    import types
+    for ps_version in ("v2", "v1"):   # 'v1' = the reference's layout without the final permute (:237-239)
+        _lib.check(lib.mjv_pixel_shuffle_layernorm(hid.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), T, S, Cv,
+                                                   1e-5, int(ps_version == "v1"), st))
+        orc = port.Oracle.__new__(port.Oracle)
+        orc.d = types.SimpleNamespace(ps_version=ps_version)
+        ps = orc.pixel_shuffle(hid[:, 1:].float().reshape(T, 32, 32, Cv), 0.5).reshape(T * 256, 4 * Cv)
+        close(out, torch.nn.functional.layer_norm(ps, (4 * Cv,), w.float(), b.float(), 1e-5).bfloat16(), ulps=1.5)
     # embedding gather skips <IMG_CONTEXT> rows
     table = torch.randn(1000, 256, device="cuda", generator=g).bfloat16()
     ids = torch.tensor([5, 999, 7, 7, 0], dtype=torch.int32, device="cuda")

@@ -75,6 +75,25 @@ def test_text_only_row_and_surplus_tiles(ref_model, capsys):
         assert torch.equal(ref[k].float(), out[k].float()), k
 
 
+def test_select_layer_and_ps_version_v1():
+    """Config knobs of the backbone: the projector reads hidden_states[select_layer] of the ViT
+    (modeling_internvl_chat.py:244-254) and ps_version 'v1' skips the final permute of pixel_shuffle (:237-241)."""
+    from oracle import reference_harness as rh
+    d = synth.dims_tiny()
+    d.vit_layers, d.select_layer, d.ps_version = 3, -2, "v1"
+    sd = synth.make_state_dict(d, seed=9)
+    m = rh.build_reference_model(d, sd)
+    pv = rh.reference_load_video(synth.make_video(33), num_segments=8, max_num=1)[0]
+    ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=25)])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = rh.reference_forward(m, pv, ids, mask)
+    out = port.Oracle(d, sd).forward(pv, ids, mask)
+    for k in ref:
+        assert torch.equal(ref[k].float(), out[k].float()), k
+
+
 def test_dynamic_ntk_rope_beyond_max_positions():
     """A padded batch longer than max_position_embeddings makes InternLM2DynamicNTKScalingRotaryEmbedding re-base theta
     for that length and keep the re-based cache for later (shorter) calls (modeling_internlm2.py:172-175, 210-231)."""

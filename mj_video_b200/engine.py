@@ -67,6 +67,7 @@ class EngineDims:
     mlp1_eps: float = 1e-5
     rope_scaling_factor: float | None = 2.0   # InternLM2 rope_scaling {'type': 'dynamic', 'factor': f}; None = no scaling
     ps_version: int = 2                        # 1 = 'v1' pixel-shuffle layout (transposed token grid)
+    rope_scaling_type: str = "dynamic"         # 'dynamic' (NTK re-basing beyond max_pos) or 'linear' (positions / factor)
 
     @staticmethod
     def from_synth(d) -> "EngineDims":
@@ -81,7 +82,8 @@ class EngineDims:
             gating_n_hidden=d.gating_n_hidden, gating_temperature=d.gating_temperature,
             aspect2criteria={k: list(v) for k, v in d.aspect2criteria.items()}, downsample_ratio=d.downsample_ratio,
             rope_scaling_factor=getattr(d, "rope_scaling_factor", 2.0),
-            ps_version=1 if getattr(d, "ps_version", "v2") == "v1" else 2)
+            ps_version=1 if getattr(d, "ps_version", "v2") == "v1" else 2,
+            rope_scaling_type=getattr(d, "rope_scaling_type", "dynamic"))
 
     @property
     def vit_seq(self) -> int:
@@ -165,7 +167,8 @@ class Engine:
             raise _lib.MjvError(f"LLM head_dim {hd} unsupported (even, <= 128)")
         rows = d.max_pos if seq_len is None else int(seq_len)
         base = d.rope_theta
-        if d.llm_arch == 0 and seq_len is not None:
+        linear = d.llm_arch == 0 and d.rope_scaling_type == "linear" and d.rope_scaling_factor is not None
+        if d.llm_arch == 0 and seq_len is not None and not linear:
             if d.rope_scaling_factor is None:
                 # the plain InternLM2RotaryEmbedding re-caches with the model's (bf16) inv_freq and bf16 positions
                 raise NotImplementedError(f"a batch of {rows} positions exceeds max_position_embeddings={d.max_pos} and "
@@ -177,6 +180,8 @@ class Engine:
         if d.llm_arch == 1 and self.rope_inv_freq_bf16:
             inv_freq = inv_freq.to(torch.bfloat16).float()
         t = torch.arange(rows, dtype=inv_freq.dtype)
+        if linear:
+            t = t / d.rope_scaling_factor   # InternLM2LinearScalingRotaryEmbedding (modeling_internlm2.py:183-199)
         freqs = torch.einsum("i,j->ij", t, inv_freq)
         cos = torch.ones((rows, 64), dtype=torch.float32)
         sin = torch.zeros((rows, 64), dtype=torch.float32)

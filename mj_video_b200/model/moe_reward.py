@@ -99,8 +99,9 @@ def _engine_dims(config) -> EngineDims:
     if config.ps_version not in ("v1", "v2"):
         raise NotImplementedError(f"ps_version {config.ps_version!r} is unknown")
     rs = lc.rope_scaling
-    if rs is not None and rs.get("type") not in ("dynamic",):
-        raise NotImplementedError(f"rope_scaling {rs} is not built")
+    if arch == "InternLM2ForCausalLM" and rs is not None and rs.get("type") not in ("dynamic", "linear"):
+        # the reference raises here as well (modeling_internlm2.py:334-335)
+        raise ValueError("Currently we only support rotary embedding's type being 'dynamic' or 'linear'.")
     return EngineDims(
         image_size=config.force_image_size or vc.image_size, patch_size=vc.patch_size, vit_hidden=vc.hidden_size,
         vit_heads=vc.num_attention_heads, vit_mlp=vc.intermediate_size, vit_layers=applied_vit_layers(vc.num_hidden_layers, config.select_layer),
@@ -113,7 +114,8 @@ def _engine_dims(config) -> EngineDims:
         aspect2criteria={k: list(v) for k, v in config.aspect2criteria.items()},
         downsample_ratio=config.downsample_ratio,
         rope_scaling_factor=(rs or {}).get("factor") if arch == "InternLM2ForCausalLM" else None,
-        ps_version=1 if config.ps_version == "v1" else 2)
+        ps_version=1 if config.ps_version == "v1" else 2,
+        rope_scaling_type=(rs or {}).get("type", "dynamic") if arch == "InternLM2ForCausalLM" else "dynamic")
 
 
 class InternVLChatRewardModeling(nn.Module):

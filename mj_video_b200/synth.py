@@ -50,6 +50,7 @@ class ModelDims:
     rope_theta: float = 1000000.0
     max_pos: int = 32768
     rope_scaling_factor: float | None = 2.0   # rope_scaling {'type': 'dynamic', 'factor': 2.0} (InternLM2 branch only)
+    rope_scaling_type: str = "dynamic"        # or 'linear' (modeling_internlm2.py:318-333)
     # projector
     downsample_ratio: float = 0.5
     select_layer: int = -1        # ViT hidden state fed to the projector (modeling_internvl_chat.py:244-254)

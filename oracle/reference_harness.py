@@ -87,7 +87,7 @@ def build_reference_config(d):
                max_position_embeddings=d.max_pos, attn_implementation="eager", use_cache=True, pad_token_id=2)
     if arch == "InternLM2ForCausalLM":
         f = getattr(d, "rope_scaling_factor", 2.0)
-        llm.update(bias=False, rope_scaling=None if f is None else {"type": "dynamic", "factor": f})
+        llm.update(bias=False, rope_scaling=None if f is None else {"type": getattr(d, "rope_scaling_type", "dynamic"), "factor": f})
     cfg = moe_reward.InternVLChatRewardModelingConfig(
         vision_config=vision, llm_config=llm, template=getattr(d, "template", "internlm2-chat"), downsample_ratio=d.downsample_ratio,
         ps_version=getattr(d, "ps_version", "v2"), select_layer=getattr(d, "select_layer", -1), force_image_size=d.image_size, num_objectives=d.num_objectives,

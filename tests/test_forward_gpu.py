@@ -474,3 +474,20 @@ def test_select_layer_and_ps_version_v1(gpu):
     d.ps_version = "v2"
     other = port.Oracle(d, sd, dtype=torch.float32, device=gpu).forward(pv.float(), ids, mask)
     assert (other["rewards"].float() - ref["rewards"].float()).abs().max().item() > 1e-3   # the layouts really differ
+
+
+def test_linear_rope_scaling(gpu):
+    """rope_scaling {'type': 'linear', 'factor': 4} (modeling_internlm2.py:183-199): host-built table, same kernels."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from mj_video_b200.engine import Engine, EngineDims
+    from oracle import port
+    d = synth.dims_tiny()
+    d.rope_scaling_type, d.rope_scaling_factor = "linear", 4.0
+    sd = synth.make_state_dict(d, seed=10, include_lm_head=False)
+    eng = Engine(EngineDims.from_synth(d), gpu)
+    eng.load_state_dict(sd)
+    pv = load_video(synth.make_video(34), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)[0]
+    ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=25)])
+    mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
+    _check(mine, port.Oracle(d, sd, dtype=torch.float32, device=gpu).forward(pv.float(), ids, mask))

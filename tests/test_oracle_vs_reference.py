@@ -94,6 +94,21 @@ def test_select_layer_and_ps_version_v1():
         assert torch.equal(ref[k].float(), out[k].float()), k
 
 
+def test_linear_rope_scaling():
+    """rope_scaling {'type': 'linear'}: positions divided by the factor (modeling_internlm2.py:183-199)."""
+    from oracle import reference_harness as rh
+    d = synth.dims_tiny()
+    d.rope_scaling_type, d.rope_scaling_factor = "linear", 4.0
+    sd = synth.make_state_dict(d, seed=10)
+    m = rh.build_reference_model(d, sd)
+    pv = rh.reference_load_video(synth.make_video(34), num_segments=8, max_num=1)[0][:2]
+    ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 2, n_cap=25)])
+    ref = rh.reference_forward(m, pv, ids, mask)
+    out = port.Oracle(d, sd).forward(pv, ids, mask)
+    for k in ref:
+        assert torch.equal(ref[k].float(), out[k].float()), k
+
+
 def test_dynamic_ntk_rope_beyond_max_positions():
     """A padded batch longer than max_position_embeddings makes InternLM2DynamicNTKScalingRotaryEmbedding re-base theta
     for that length and keep the re-based cache for later (shorter) calls (modeling_internlm2.py:172-175, 210-231)."""

@@ -157,3 +157,31 @@ def test_get_index_matches():
     mod = rh.reference_data_module()
     for (bound, fps, mf, ns) in [(None, 8.0, 15, 8), (None, 30.0, 299, 32), ((1.0, 4.5), 24.0, 200, 16), (None, 8.0, 7, 8)]:
         assert (mod.get_index(bound, fps, mf, 0, ns) == port.get_index(bound, fps, mf, 0, ns)).all()
+
+
+def test_prepare_chat_input_matches_reference_with_history():
+    """The drop-in `prepare_chat_input` (modeling_internvl_chat.py:36-89) token for token, including multi-turn history,
+    per-frame tile counts and the mutated generation_config, under the same stub tokenizer."""
+    from oracle import reference_harness as rh
+    from oracle.make_golden import StubTokenizer
+    from mj_video_b200.model import InternVLChatRewardModelingConfig, prepare_chat_input
+    _, _, chat = rh.reference_modules()
+    d = synth.dims_tiny()
+    cfg_ref = rh.build_reference_config(d)
+    cfg_mine = InternVLChatRewardModelingConfig(
+        vision_config=cfg_ref.vision_config.to_dict(), llm_config=cfg_ref.llm_config.to_dict(), template="internlm2-chat",
+        downsample_ratio=0.5, ps_version="v2", select_layer=-1, force_image_size=448, num_objectives=28, num_aspects=5,
+        aspect2criteria=d.aspect2criteria, gating_temperature=1.0, gating_hidden_dim=d.gating_hidden, gating_n_hidden=3)
+    tok = StubTokenizer()
+    pv = torch.zeros(8, 3, 448, 448)
+    cases = [dict(question="<image>\nhello", history=[("<image>\nfirst q", "first a")], npl=[4, 4]),
+             dict(question="what?", history=[("q1", "a1"), ("q2", "a2")], npl=None),
+             dict(question="Frame1: <image>\nFrame2: <image>\ncap", history=None, npl=[3, 5], return_history=True)]
+    for c in cases:
+        g1, g2 = {}, {}
+        kw = dict(history=c["history"], return_history=c.get("return_history", False), num_patches_list=c["npl"])
+        ref = chat.prepare_chat_input(cfg_ref, tok, pv if c["npl"] else None, c["question"], g1, **kw)
+        got = prepare_chat_input(cfg_mine, tok, pv if c["npl"] else None, c["question"], g2, **kw)
+        assert len(ref) == len(got) and g1 == g2
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b) if torch.is_tensor(a) else a == b

@@ -90,6 +90,50 @@ class _AvReader:
         return np.stack([self.frames[int(i)] for i in indices])
 
 
+class _OpenCVReader:
+    """cv2.VideoCapture fallback (the container ships OpenCV but neither decord nor PyAV). Frames are decoded in index
+    order while walking the stream once — robust for codecs whose random seeking is inexact."""
+
+    def __init__(self, path):
+        import cv2
+        self.cv2 = cv2
+        self.path = str(path)
+        cap = cv2.VideoCapture(self.path)
+        if not cap.isOpened():
+            raise RuntimeError(f"OpenCV cannot open {self.path}")
+        self.n = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        self.fps = float(cap.get(cv2.CAP_PROP_FPS)) or 25.0
+        cap.release()
+        if self.n <= 0:
+            raise RuntimeError(f"{self.path}: no frames")
+
+    def __len__(self):
+        return self.n
+
+    def get_avg_fps(self):
+        return self.fps
+
+    def take(self, indices) -> np.ndarray:
+        cv2 = self.cv2
+        want = [int(i) for i in indices]
+        order = sorted(set(want))
+        got = {}
+        cap = cv2.VideoCapture(self.path)
+        pos = 0
+        for target in order:
+            while pos < target:       # skip without decoding to RGB
+                if not cap.grab():
+                    break
+                pos += 1
+            ok, frame = cap.read()
+            pos += 1
+            if not ok:
+                raise RuntimeError(f"{self.path}: cannot decode frame {target}")
+            got[target] = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+        cap.release()
+        return np.stack([got[i] for i in want])
+
+
 def open_video(video):
     """Frame source with `len`, `get_avg_fps`, `take(indices) -> uint8 [n,H,W,3]`."""
     if isinstance(video, (np.ndarray, torch.Tensor)):
@@ -108,8 +152,12 @@ def open_video(video):
         pass
     try:
         return _AvReader(path)
+    except ImportError:
+        pass
+    try:
+        return _OpenCVReader(path)
     except ImportError as e:
-        raise RuntimeError("no video decoder available (decord / av not installed); pass an array or .npy") from e
+        raise RuntimeError("no video decoder available (decord / av / cv2 not installed); pass an array or .npy") from e
 
 
 def preprocess_frames(frames_u8: torch.Tensor, input_size=448, max_num=1, use_thumbnail=True,

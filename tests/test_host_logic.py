@@ -219,3 +219,34 @@ def test_safetensors_checkpoint_roundtrip(tmp_path):
     assert fe.final and n == len(keys) - 1 and "model.language_model.output.weight" not in fe.keys
     with pytest.raises(FileNotFoundError):
         checkpoint.checkpoint_files(str(tmp_path / "missing"))
+
+
+def test_opencv_reader_decodes_a_real_file(tmp_path):
+    """`load_video(path)` on an actual video file: the OpenCV reader (the image has no decord / PyAV) returns the frames
+    `get_index` selects, in RGB, identical to decoding the whole file and indexing."""
+    cv2 = pytest.importorskip("cv2")
+    from mj_video_b200.data_processor import data as dp
+    path = str(tmp_path / "clip.avi")
+    vid = synth.make_video(5, n_frames=12, height=96, width=128)
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 8.0, (128, 96))
+    if not wr.isOpened():
+        pytest.skip("this OpenCV build cannot write MJPG/AVI")
+    for f in vid:
+        wr.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    wr.release()
+    rd = dp._OpenCVReader(path)
+    assert len(rd) == 12 and abs(rd.get_avg_fps() - 8.0) < 1e-3
+    cap = cv2.VideoCapture(path)
+    allf = []
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        allf.append(cv2.cvtColor(fr, cv2.COLOR_BGR2RGB))
+    cap.release()
+    idx = dp.get_index(None, rd.get_avg_fps(), len(rd) - 1, first_idx=0, num_segments=5)
+    got = rd.take(idx)
+    assert got.shape == (5, 96, 128, 3) and got.dtype == np.uint8
+    assert all(np.array_equal(got[k], allf[int(i)]) for k, i in enumerate(idx))
+    assert np.abs(got[0].astype(int) - vid[int(idx[0])].astype(int)).mean() < 12     # MJPG is lossy but close
+    assert isinstance(dp.open_video(path), (dp._OpenCVReader, dp._DecordReader, dp._AvReader))

@@ -45,3 +45,29 @@ def test_large_batch_identity_path_roundtrip(built_lib):
     # the reference normalises on the CPU (IEEE division; CUDA's scalar div may use a reciprocal multiply)
     ref = (frames[:4].cpu().permute(0, 3, 1, 2).float().div(255) - mean.cpu()) / std.cpu()
     assert torch.equal(out[:4].cpu(), ref)
+
+
+def test_load_video_from_a_real_file(built_lib, tmp_path):
+    """The reference call `load_video(path, num_segments, max_num)` (data.py:158-179) on an actual video file: host decode
+    (OpenCV here), get_index sampling, then the CUDA resize / tile / normalise kernels — bit-identical to the oracle's frame
+    path applied to the same decoded frames."""
+    cv2 = pytest.importorskip("cv2")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import data as dp, load_video
+    from oracle import port
+    path = str(tmp_path / "clip.avi")
+    vid = synth.make_video(6, n_frames=10, height=360, width=640)
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 8.0, (640, 360))
+    if not wr.isOpened():
+        pytest.skip("this OpenCV build cannot write MJPG/AVI")
+    for f in vid:
+        wr.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    wr.release()
+    rd = dp.open_video(path)
+    decoded = rd.take(range(len(rd)))
+    pv, counts = load_video(path, num_segments=4, max_num=6)
+    ref_pv, ref_counts = port.load_video_frames(decoded, num_segments=4, max_num=6, fps=rd.get_avg_fps())
+    assert counts == ref_counts and pv.shape == ref_pv.shape and pv.dtype == torch.float32 and pv.device.type == "cpu"
+    assert torch.equal(pv, ref_pv)

@@ -86,6 +86,8 @@ typedef struct mjv_gemm_desc {
     int32_t heads;
     int32_t debug;        /* perf experiments only (0 in production)                 */
     int32_t cta_group;    /* 0 = auto (CTA pairs when block_n = 256), 1 or 2         */
+    int32_t v_head_dim;   /* QKV_LLM: columns per V head in the N layout and rows per V^T plane (0 = 128); a multiple of
+                             32 — V needs no rotary slot, so narrow heads (e.g. 96) are packed                          */
 } mjv_gemm_desc;
 
 int mjv_gemm_bf16(const mjv_gemm_desc* desc, void* stream);
@@ -120,6 +122,10 @@ typedef struct mjv_attn_desc {
     int32_t n_work;
     float scale;          /* softmax scale (1/sqrt(head_dim))                                             */
     double flops_hint;    /* varlen: algorithmic FLOPs of this launch for the profiler (0 = unknown)      */
+    /* Heads narrower than the 64/128 tile (e.g. 96): q/k stay in head_dim-wide slots, but
+     *   v_head_dim   rows per V^T plane (0 = head_dim); rows beyond it are zero-filled by TMA,
+     *   out_head_dim columns per head written to `out` (0 = head_dim; a multiple of 32), head h at column h*out_head_dim. */
+    int32_t v_head_dim, out_head_dim;
 } mjv_attn_desc;
 
 int mjv_attention(const mjv_attn_desc* desc, void* stream);

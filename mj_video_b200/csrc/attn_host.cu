@@ -33,6 +33,10 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     const int hd = d.head_dim;
     const int bkv = attn_detail::BKV;
 
+    const int v_hd = d.v_head_dim > 0 ? d.v_head_dim : hd;
+    const int out_hd = d.out_head_dim > 0 ? d.out_head_dim : hd;
+    MJV_CHECK(v_hd <= hd && out_hd <= hd && out_hd % 32 == 0, MJV_ERR_ARG,
+              "attention: v_head_dim %d / out_head_dim %d must fit the %d-wide tile (out a multiple of 32)", v_hd, out_hd, hd);
     CUtensorMap tq, tk, tv;
     if (varlen) {
         uint64_t qd[3] = {(uint64_t)(d.q_col0 + d.heads * hd), (uint64_t)d.total_rows, 1};
@@ -43,7 +47,8 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
         uint64_t ks[3] = {1, (uint64_t)d.ldk, (uint64_t)d.ldk * (uint64_t)d.total_rows};
         uint32_t kb[3] = {64, (uint32_t)bkv, 1};
         MJV_PROPAGATE(make_tmap_bf16(&tk, d.k, 3, kd, ks, kb));
-        uint64_t vd[3] = {(uint64_t)(d.vt_cols > 0 ? d.vt_cols : d.total_rows), (uint64_t)hd, (uint64_t)d.kv_heads};
+        // rows beyond v_hd do not exist in the plane: the box still spans hd rows and TMA zero-fills the rest
+        uint64_t vd[3] = {(uint64_t)(d.vt_cols > 0 ? d.vt_cols : d.total_rows), (uint64_t)v_hd, (uint64_t)d.kv_heads};
         uint64_t vs[3] = {1, (uint64_t)d.vt_ld, (uint64_t)d.vt_plane_stride};
         uint32_t vb[3] = {64, (uint32_t)hd, 1};
         MJV_PROPAGATE(make_tmap_bf16(&tv, d.vt, 3, vd, vs, vb));
@@ -56,7 +61,7 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
         uint64_t ks[3] = {1, (uint64_t)d.ldk, (uint64_t)d.ldk * (uint64_t)d.seq_len};
         uint32_t kb[3] = {64, (uint32_t)bkv, 1};
         MJV_PROPAGATE(make_tmap_bf16(&tk, d.k, 3, kd, ks, kb));
-        uint64_t vd[3] = {(uint64_t)d.seq_len, (uint64_t)hd, (uint64_t)d.nseq * (uint64_t)d.heads};
+        uint64_t vd[3] = {(uint64_t)d.seq_len, (uint64_t)v_hd, (uint64_t)d.nseq * (uint64_t)d.heads};
         uint64_t vs[3] = {1, (uint64_t)d.vt_ld, (uint64_t)d.vt_plane_stride};
         uint32_t vb[3] = {64, (uint32_t)hd, 1};
         MJV_PROPAGATE(make_tmap_bf16(&tv, d.vt, 3, vd, vs, vb));
@@ -77,6 +82,7 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     a.ldo = (int)d.ldo;
     a.scale_log2 = d.scale * 1.4426950408889634f;
     a.batched = varlen ? 0 : 1;
+    a.out_hd = out_hd;
 
     // algorithmic FLOPs: 4*heads*hd*S^2 per sequence (bidirectional); causal work is supplied by the caller (flops_hint)
     double work = d.flops_hint;

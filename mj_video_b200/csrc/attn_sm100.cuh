@@ -41,6 +41,7 @@ struct AttnArgs {
     int ldo;
     float scale_log2;       // softmax scale * log2(e)
     int batched;            // 1: maps carry a per-sequence batch dim and rows are sequence-relative (ViT)
+    int out_hd;             // columns per head written to `out` (<= HD, multiple of 16): narrow heads are stored packed
 };
 
 namespace attn_detail {
@@ -429,9 +430,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             ptx::tc_fence_after();
             if (warp_has_rows) {
                 const float inv = 1.0f / l_run;
-                __nv_bfloat16* dst = args.out + static_cast<long long>(t.row_base + qrow) * args.ldo + t.h * HD;
+                __nv_bfloat16* dst = args.out + static_cast<long long>(t.row_base + qrow) * args.ldo + t.h * args.out_hd;
 #pragma unroll 1
                 for (int c = 0; c < HD / 32; ++c) {
+                    if (c * 32 >= args.out_hd) break;  // columns beyond the model's head_dim are exact zeros: not stored
                     uint32_t o[32];
                     ptx::tmem_ld_x32(tmem_O + lane_sel + c * 32, o);
                     ptx::tmem_wait_ld();

@@ -109,6 +109,19 @@ size_t dtype_size(int dt) { return dt == MJV_DTYPE_F32 ? 4 : 2; }
 // permutation is applied to q and k alike, so q.k is unchanged; `wo` gets matching zero columns.
 constexpr int kHeadSlot = 128;
 inline int qk_slot_dim(int d, int hd) { return d < hd / 2 ? d : 64 + (d - hd / 2); }
+// V needs no rotary slot and the attention output no padding: when head_dim is a multiple of 32 (e.g. 96) V heads are
+// packed in the QKV GEMM's N (if the total stays a multiple of the 128-column tile) and the attention kernel writes only
+// head_dim columns per head, so `wo` keeps its original K.
+inline int v_head_width(const mjv_config& c) {
+    const int hd = c.llm_hidden / c.llm_heads;
+    if (hd % 32 != 0) return kHeadSlot;
+    const long long n = static_cast<long long>(c.llm_heads + c.llm_kv_heads) * kHeadSlot + static_cast<long long>(c.llm_kv_heads) * hd;
+    return n % 128 == 0 ? hd : kHeadSlot;
+}
+inline int o_head_width(const mjv_config& c) {
+    const int hd = c.llm_hidden / c.llm_heads;
+    return hd % 32 == 0 ? hd : kHeadSlot;
+}
 
 bool ends_with(const std::string& s, const char* suf) {
     const size_t n = strlen(suf);
@@ -194,6 +207,9 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
 
     const int hd = c.llm_hidden / c.llm_heads;
     const int hs = kHeadSlot;
+    const int hv = v_head_width(c), ho = o_head_width(c);
+    const long long v_base = static_cast<long long>(c.llm_heads + c.llm_kv_heads) * hs;  // first V row of the fused weight
+    const long long qkv_rows = v_base + static_cast<long long>(c.llm_kv_heads) * hv;
     std::string dst_key = key;
     long long dst_rows = rows, dst_ld = cols;
     std::vector<int> row_map, col_map;
@@ -204,7 +220,7 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
         const int g = c.llm_heads / c.llm_kv_heads;
         MJV_CHECK(rows == static_cast<long long>(c.llm_heads + 2 * c.llm_kv_heads) * hd, MJV_ERR_ARG,
                   "%s: unexpected rows %lld", key.c_str(), rows);
-        dst_rows = static_cast<long long>(c.llm_heads + 2 * c.llm_kv_heads) * hs;
+        dst_rows = qkv_rows;
         row_map.resize(rows);
         for (int kv = 0; kv < c.llm_kv_heads; ++kv)
             for (int s = 0; s < g + 2; ++s)
@@ -213,28 +229,28 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
                     int dst;
                     if (s < g) dst = (kv * g + s) * hs + qk_slot_dim(d, hd);
                     else if (s == g) dst = (c.llm_heads + kv) * hs + qk_slot_dim(d, hd);
-                    else dst = (c.llm_heads + c.llm_kv_heads + kv) * hs + d;
+                    else dst = static_cast<int>(v_base) + kv * hv + d;
                     row_map[src] = dst;
                 }
     } else if (ends_with(key, "attention.wq.weight") || ends_with(key, "attention.wk.weight") ||
                ends_with(key, "attention.wv.weight")) {
         const char which = key[key.size() - 8];  // 'q' / 'k' / 'v'
         dst_key = key.substr(0, key.size() - 9) + "wqkv.weight";
-        dst_rows = static_cast<long long>(c.llm_heads + 2 * c.llm_kv_heads) * hs;
+        dst_rows = qkv_rows;
         const int n_heads = which == 'q' ? c.llm_heads : c.llm_kv_heads;
         MJV_CHECK(rows == static_cast<long long>(n_heads) * hd, MJV_ERR_ARG, "%s: unexpected rows %lld", key.c_str(), rows);
         const int base = which == 'q' ? 0 : (which == 'k' ? c.llm_heads : c.llm_heads + c.llm_kv_heads);
         row_map.resize(rows);
         for (long long r = 0; r < rows; ++r) {
             const int head = static_cast<int>(r / hd), d = static_cast<int>(r % hd);
-            row_map[r] = (base + head) * hs + (which == 'v' ? d : qk_slot_dim(d, hd));
+            row_map[r] = which == 'v' ? static_cast<int>(v_base) + head * hv + d : (base + head) * hs + qk_slot_dim(d, hd);
         }
     } else if (ends_with(key, "attention.wo.weight")) {
         MJV_CHECK(cols == static_cast<long long>(c.llm_heads) * hd, MJV_ERR_ARG, "%s: unexpected cols %lld", key.c_str(), cols);
-        dst_ld = static_cast<long long>(c.llm_heads) * hs;
-        if (hd != hs) {
+        dst_ld = static_cast<long long>(c.llm_heads) * ho;
+        if (hd != ho) {
             col_map.resize(cols);
-            for (long long cc = 0; cc < cols; ++cc) col_map[cc] = static_cast<int>((cc / hd) * hs + cc % hd);
+            for (long long cc = 0; cc < cols; ++cc) col_map[cc] = static_cast<int>((cc / hd) * ho + cc % hd);
         }
     } else if (ends_with(key, "feed_forward.w1.weight") || ends_with(key, "feed_forward.w3.weight")) {
         // gate/up interleaved in 32-row chunks so one GEMM tile holds both halves of SwiGLU
@@ -369,7 +385,8 @@ int finalize(mjv_handle* h) {
 // ------------------------------------------------------------------------------------------------ sizes
 struct Dims {
     int S, P, C, Fv, heads, Kpad, Spad, tok_per_tile;
-    int D, F, Hq, Hkv, hd, hs;  // hd: model head_dim; hs: stored head slot (128)
+    int D, F, Hq, Hkv, hd, hs;  // hd: model head_dim; hs: stored head slot of q / k (128)
+    int hv, ho;                 // stored width of a V head (N of the QKV GEMM, rows of a V^T plane) and of an output head
 };
 Dims dims_of(const mjv_handle* h) {
     const mjv_config& c = h->cfg;
@@ -389,6 +406,8 @@ Dims dims_of(const mjv_handle* h) {
     d.Hkv = c.llm_kv_heads;
     d.hd = c.llm_hidden / c.llm_heads;
     d.hs = kHeadSlot;
+    d.hv = v_head_width(c);
+    d.ho = o_head_width(c);
     return d;
 }
 inline size_t al(size_t bytes) { return (bytes + 1023) & ~size_t(1023); }
@@ -561,14 +580,16 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
     MJV_CHECK(M > 0 && M < (1LL << 31) / 16, MJV_ERR_ARG, "bad token count %lld", M);
     MJV_CHECK(b.max_seq_len > 0 && b.max_seq_len <= h->rope_rows, MJV_ERR_ARG,
               "longest sequence (%d tokens) exceeds the loaded RoPE table (%lld rows)", b.max_seq_len, h->rope_rows);
-    const int nq = d.Hq * d.hs, nk = d.Hkv * d.hs;
+    const int nq = d.Hq * d.hs, nk = d.Hkv * d.hs;   // q / k columns (128-wide rotary slots)
+    const int nv = d.Hkv * d.hv;                      // V columns of the QKV GEMM (packed heads)
+    const int no = d.Hq * d.ho;                       // attention output columns = K of `wo`
     __nv_bfloat16* hcur = static_cast<__nv_bfloat16*>(embeds);
     MJV_ALLOC(xn, __nv_bfloat16*, ar, static_cast<size_t>(M) * d.D * 2);
     MJV_ALLOC(q, __nv_bfloat16*, ar, static_cast<size_t>(M) * nq * 2);
     MJV_ALLOC(k, __nv_bfloat16*, ar, static_cast<size_t>(M) * nk * 2);
-    const size_t vt_bytes = static_cast<size_t>(d.Hkv) * d.hs * b.vt_cols * 2;
+    const size_t vt_bytes = static_cast<size_t>(d.Hkv) * d.hv * b.vt_cols * 2;
     MJV_ALLOC(vt, __nv_bfloat16*, ar, vt_bytes);
-    MJV_ALLOC(att, __nv_bfloat16*, ar, static_cast<size_t>(M) * nq * 2);
+    MJV_ALLOC(att, __nv_bfloat16*, ar, static_cast<size_t>(M) * no * 2);
     MJV_ALLOC(mid, __nv_bfloat16*, ar, static_cast<size_t>(M) * d.F * 2);
     // alignment-pad columns of V^T are never written: keep them finite (they are multiplied by exact zeros)
     MJV_CUDA_OK(cudaMemsetAsync(vt, 0, vt_bytes, st));
@@ -576,7 +597,7 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
     // compact buffers of the last layer: only the 2 rows per sample the head reads go through wo / MLP / final norm
     const int G2 = 2 * b.n_rows;
     const bool shortcut = b.work_last != nullptr && b.n_work_last > 0;
-    MJV_ALLOC(att_c, __nv_bfloat16*, ar, static_cast<size_t>(G2) * nq * 2);
+    MJV_ALLOC(att_c, __nv_bfloat16*, ar, static_cast<size_t>(G2) * no * 2);
     MJV_ALLOC(h_c, __nv_bfloat16*, ar, static_cast<size_t>(G2) * d.D * 2);
     MJV_ALLOC(xn_c, __nv_bfloat16*, ar, static_cast<size_t>(G2) * d.D * 2);
     MJV_ALLOC(mid_c, __nv_bfloat16*, ar, static_cast<size_t>(G2) * d.F * 2);
@@ -586,7 +607,8 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
         const bool last = shortcut && (i == c.llm_layers - 1);
         MJV_PROPAGATE(rmsnorm(hcur, w.attn_norm, xn, M, d.D, c.rms_eps, nullptr, st));
         {
-            mjv_gemm_desc g = gemm_base(xn, d.D, w.wqkv, d.D, q, nq, (int)M, nq + 2 * nk, d.D, MJV_EPI_QKV_LLM);
+            mjv_gemm_desc g = gemm_base(xn, d.D, w.wqkv, d.D, q, nq, (int)M, nq + nk + nv, d.D, MJV_EPI_QKV_LLM);
+            g.v_head_dim = d.hv;
             g.out_k = k;
             g.out_vt = vt;
             g.rope_cos = h->rope_cos;
@@ -595,7 +617,7 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
             g.row_vt = b.row_vt;
             g.n_q_cols = nq;
             g.n_k_cols = nk;
-            g.vt_stride_head = static_cast<long long>(d.hs) * b.vt_cols;
+            g.vt_stride_head = static_cast<long long>(d.hv) * b.vt_cols;
             g.vt_ld = static_cast<int>(b.vt_cols);
             MJV_PROPAGATE(gemm_bf16(g, st));
         }
@@ -608,9 +630,11 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
             a.out = att;
             a.ldq = nq;
             a.ldk = nk;
-            a.ldo = nq;
+            a.ldo = no;
+            a.out_head_dim = d.ho;
+            a.v_head_dim = d.hv;
             a.vt_ld = b.vt_cols;
-            a.vt_plane_stride = static_cast<long long>(d.hs) * b.vt_cols;
+            a.vt_plane_stride = static_cast<long long>(d.hv) * b.vt_cols;
             a.total_rows = M;
             a.head_dim = d.hs;
             a.heads = d.Hq;
@@ -633,7 +657,7 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
         __nv_bfloat16* mid_in = mid;
         int rows = (int)M;
         if (last) {
-            MJV_PROPAGATE(gather_rows(att, b.gather_rows, att_c, G2, nq, st));
+            MJV_PROPAGATE(gather_rows(att, b.gather_rows, att_c, G2, no, st));
             MJV_PROPAGATE(gather_rows(hcur, b.gather_rows, h_c, G2, d.D, st));
             hres = h_c;
             att_in = att_c;
@@ -642,7 +666,7 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
             rows = G2;
         }
         {
-            mjv_gemm_desc g = gemm_base(att_in, nq, w.wo, nq, hres, d.D, rows, d.D, nq, MJV_EPI_RESID);
+            mjv_gemm_desc g = gemm_base(att_in, no, w.wo, no, hres, d.D, rows, d.D, no, MJV_EPI_RESID);
             g.residual = hres;
             g.ldr = d.D;
             MJV_PROPAGATE(gemm_bf16(g, st));

@@ -74,6 +74,9 @@ int gemm_bf16(const mjv_gemm_desc& d, cudaStream_t stream) {
         MJV_CHECK(d.n_q_cols % 128 == 0 && d.n_k_cols % 128 == 0 && d.rope_cos && d.rope_sin && d.row_pos &&
                       d.out_k && d.out_vt,
                   MJV_ERR_ARG, "gemm: QKV_LLM needs head_dim 128 and rope tables");
+        const int v_hd = d.v_head_dim > 0 ? d.v_head_dim : 128;
+        MJV_CHECK(v_hd % 32 == 0 && v_hd <= 128 && (d.N - d.n_q_cols - d.n_k_cols) % v_hd == 0, MJV_ERR_ARG,
+                  "gemm: QKV_LLM v_head_dim %d must be a multiple of 32 dividing the V columns", v_hd);
     }
     if (d.epilogue == EPI_QKV_VIT)
         MJV_CHECK(d.bias && d.out_vt && d.seq > 0 && d.heads > 0, MJV_ERR_ARG, "gemm: QKV_VIT needs bias/out_vt");
@@ -122,6 +125,7 @@ int gemm_bf16(const mjv_gemm_desc& d, cudaStream_t stream) {
     a.seq = d.seq;
     a.heads = d.heads;
     a.debug = d.debug;
+    a.v_hd = d.v_head_dim > 0 ? d.v_head_dim : 128;
 
     // output tensor maps for the TMA-store epilogue (BN == 256): [32 rows x 64 columns] boxes, 128B swizzle
     CUtensorMap tmO, tmO2;

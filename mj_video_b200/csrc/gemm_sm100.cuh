@@ -53,6 +53,7 @@ struct GemmArgs {
     int seq;                   // QKV_VIT: tokens per tile (1025); PATCH: patches per tile (1024)
     int heads;                 // QKV_VIT: heads
     int debug;                 // perf experiments only: 1 = epilogue skips TMEM loads and stores, 2 = loads but no stores
+    int v_hd;                  // QKV_LLM: columns per V head in N and rows per V^T plane (multiple of 32, <= 128)
 };
 
 namespace gemm_detail {
@@ -503,21 +504,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             stg_store(tm, ncol + 64, m0 + q * 32);  // columns 64..127
                         }
                     } else {
-                        // V head: transposed store, V^T[head][d][token]
-                        const int vcol = n - args.n_q_cols - args.n_k_cols;  // head*128
+                        // V columns: transposed store, V^T[head][d][token]. V heads are v_hd (a multiple of 32) columns wide
+                        // in N — narrower than the 128-wide rotary slots of q and k when the model's head_dim is — so a
+                        // 32-column chunk never straddles two heads.
+                        const int vcol0 = n - args.n_q_cols - args.n_k_cols;  // first V column of this 128-column group
                         const int vtc = (row_ok && args.row_vt != nullptr) ? args.row_vt[row] : row;
-                        __nv_bfloat16* dst = args.out_vt + static_cast<long long>(vcol >> 7) * args.vt_stride_head + vtc;
                         const int cb = kTma ? 0 : half * 64;
                         const int ce = kTma ? 128 : half * 64 + 64;
 #pragma unroll 1
                         for (int c = cb; c < ce; c += 32) {
+                            if (n + c >= args.N) break;  // the last group may be partial when v_hd < 128
                             uint32_t v[32];
                             ptx::tmem_ld_x32(t_base + h0 + c, v);
                             ptx::tmem_wait_ld();
+                            const int vhead = (vcol0 + c) / args.v_hd;
+                            const int d0 = (vcol0 + c) - vhead * args.v_hd;
+                            __nv_bfloat16* dst = args.out_vt + static_cast<long long>(vhead) * args.vt_stride_head +
+                                                 static_cast<long long>(d0) * args.vt_ld + vtc;
                             if (row_ok) {
 #pragma unroll
                                 for (int i = 0; i < 32; ++i)
-                                    dst[static_cast<long long>(c + i) * args.vt_ld] = __float2bfloat16_rn(__uint_as_float(v[i]));
+                                    dst[static_cast<long long>(i) * args.vt_ld] = __float2bfloat16_rn(__uint_as_float(v[i]));
                             }
                         }
                     }

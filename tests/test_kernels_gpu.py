@@ -136,6 +136,36 @@ def test_gemm_qkv_epilogues(ops):
     close(vt[:, :, row_vt.long()], y[:, (Hq + Hkv) * 128:].reshape(tot, Hkv, 128).permute(1, 2, 0))
 
 
+def test_gemm_qkv_llm_packed_v_heads(ops):
+    """QKV_LLM with V heads narrower than the rotary slot (v_head_dim 96): q/k in 128-wide slots with RoPE, V columns packed
+    96 per head in N and stored as V^T planes of 96 rows."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    tot, D, Hq, Hkv, hv = 500, 256, 4, 4, 96
+    N = (Hq + Hkv) * 128 + Hkv * hv          # 1408 = 11 x 128
+    x = (torch.randn(tot, D, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, D, device="cuda", generator=g) * 0.1).bfloat16()
+    pos = (torch.arange(tot, device="cuda") % 333).int()
+    inv = 1.0 / (1e4 ** (torch.arange(0, 128, 2, device="cuda").float() / 128))
+    fr = torch.outer(torch.arange(512, device="cuda").float(), inv)
+    cos, sin = fr.cos().bfloat16().float().contiguous(), fr.sin().bfloat16().float().contiguous()
+    vt_cols = (tot + 7) // 8 * 8
+    qo = torch.zeros(tot, Hq * 128, device="cuda", dtype=torch.bfloat16)
+    ko = torch.zeros(tot, Hkv * 128, device="cuda", dtype=torch.bfloat16)
+    vt = torch.zeros(Hkv, hv, vt_cols, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, w, out=qo, epilogue=ops.EPI_QKV_LLM, out_k=ko, out_vt=vt, rope_cos=cos, rope_sin=sin, row_pos=pos,
+             n_q_cols=Hq * 128, n_k_cols=Hkv * 128, vt_stride_head=hv * vt_cols, vt_ld=vt_cols, v_head_dim=hv)
+    y = mm(x, w).bfloat16()
+
+    def rope(t):
+        c = torch.cat([cos, cos], -1)[pos.long()].bfloat16()[:, None, :]
+        s_ = torch.cat([sin, sin], -1)[pos.long()].bfloat16()[:, None, :]
+        return (t * c) + (torch.cat([-t[..., 64:], t[..., :64]], -1) * s_)
+
+    close(qo, rope(y[:, :Hq * 128].reshape(tot, Hq, 128)).reshape(tot, -1))
+    close(ko, rope(y[:, Hq * 128:(Hq + Hkv) * 128].reshape(tot, Hkv, 128)).reshape(tot, -1))
+    close(vt[:, :, :tot], y[:, (Hq + Hkv) * 128:].reshape(tot, Hkv, hv).permute(1, 2, 0))
+
+
 def ref_attn(q, k, v, causal, scale):
     H, Hkv = q.shape[1], k.shape[1]
     k = k.repeat_interleave(H // Hkv, dim=1)
@@ -188,6 +218,36 @@ def test_attention_causal_varlen_gqa(ops, lens, H, Hkv):
     refs, o = [], 0
     for n in lens:
         refs.append(ref_attn(q[o:o + n].float(), k[o:o + n].float(), v[o:o + n].float(), True, 1 / math.sqrt(128)))
+        o += n
+    assert (out.float() - torch.cat(refs)).abs().max().item() < 2e-2
+
+
+def test_attention_narrow_heads_packed_v_and_output(ops):
+    """head_dim 96 served by the 128-wide tile: q/k in 128-wide slots, V^T planes of 96 rows (TMA zero-fills the rest of
+    the box), only 96 output columns per head written, head h at column 96*h (mjv_attn_desc.v_head_dim / out_head_dim)."""
+    lens, H, Hkv, hd = [300, 77, 129], 4, 2, 96
+    g = torch.Generator(device="cuda").manual_seed(11)
+    tot = sum(lens)
+    q = torch.zeros(tot, H, 128, device="cuda", dtype=torch.bfloat16)
+    k = torch.zeros(tot, Hkv, 128, device="cuda", dtype=torch.bfloat16)
+    q[..., :hd] = torch.randn(tot, H, hd, device="cuda", generator=g).bfloat16()
+    k[..., :hd] = torch.randn(tot, Hkv, hd, device="cuda", generator=g).bfloat16()
+    v = torch.randn(tot, Hkv, hd, device="cuda", generator=g).bfloat16()
+    starts, vt_cols = ops.vt_layout(lens)
+    vt = torch.zeros(Hkv, hd, vt_cols, device="cuda", dtype=torch.bfloat16)
+    o = 0
+    for st, n in zip(starts, lens):
+        vt[:, :, st:st + n] = v[o:o + n].permute(1, 2, 0)
+        o += n
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    out = torch.full((tot, H * hd), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q.reshape(tot, -1), k.reshape(tot, -1), vt, out, head_dim=128, heads=H, kv_heads=Hkv, causal=True,
+                  scale=1 / math.sqrt(hd), cu_seqlens=cu, work=ops.causal_work_list(lens).cuda(),
+                  vt_starts=torch.tensor(starts, dtype=torch.int32, device="cuda"), vt_cols=vt_cols, v_head_dim=hd,
+                  out_head_dim=hd)
+    refs, o = [], 0
+    for n in lens:
+        refs.append(ref_attn(q[o:o + n, :, :hd].float(), k[o:o + n, :, :hd].float(), v[o:o + n].float(), True, 1 / math.sqrt(hd)))
         o += n
     assert (out.float() - torch.cat(refs)).abs().max().item() < 2e-2
 

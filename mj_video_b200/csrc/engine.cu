@@ -115,8 +115,13 @@ inline int qk_slot_dim(int d, int hd) { return d < hd / 2 ? d : 64 + (d - hd / 2
 inline int v_head_width(const mjv_config& c) {
     const int hd = c.llm_hidden / c.llm_heads;
     if (hd % 32 != 0) return kHeadSlot;
-    const long long n = static_cast<long long>(c.llm_heads + c.llm_kv_heads) * kHeadSlot + static_cast<long long>(c.llm_kv_heads) * hd;
-    return n % 128 == 0 ? hd : kHeadSlot;
+    const long long qk = static_cast<long long>(c.llm_heads + c.llm_kv_heads) * kHeadSlot;
+    const long long packed = qk + static_cast<long long>(c.llm_kv_heads) * hd;
+    const long long padded = qk + static_cast<long long>(c.llm_kv_heads) * kHeadSlot;
+    // keep the 256-column CTA-pair tile whenever the padded layout would have it
+    if (packed % 256 == 0) return hd;
+    if (padded % 256 != 0 && packed % 128 == 0) return hd;
+    return kHeadSlot;
 }
 inline int o_head_width(const mjv_config& c) {
     const int hd = c.llm_hidden / c.llm_heads;

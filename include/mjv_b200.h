@@ -84,7 +84,6 @@ typedef struct mjv_gemm_desc {
     int32_t vt_ld;
     int32_t seq;
     int32_t heads;
-    int32_t debug;        /* perf experiments only (0 in production)                 */
     int32_t cta_group;    /* 0 = auto (CTA pairs when block_n = 256), 1 or 2         */
     int32_t v_head_dim;   /* QKV_LLM: columns per V head in the N layout and rows per V^T plane (0 = 128); a multiple of
                              32 — V needs no rotary slot, so narrow heads (e.g. 96) are packed                          */

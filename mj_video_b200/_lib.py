@@ -30,7 +30,7 @@ class GemmDesc(C.Structure):
         ("row_pos", C.c_void_p), ("row_map", C.c_void_p), ("row_vt", C.c_void_p), ("pos_emb", C.c_void_p),
         ("n_q_cols", C.c_int32), ("n_k_cols", C.c_int32),
         ("vt_stride_head", C.c_int64), ("vt_ld", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32),
-        ("debug", C.c_int32), ("cta_group", C.c_int32), ("v_head_dim", C.c_int32),
+        ("cta_group", C.c_int32), ("v_head_dim", C.c_int32),
     ]
 
 

@@ -124,7 +124,6 @@ int gemm_bf16(const mjv_gemm_desc& d, cudaStream_t stream) {
     a.vt_ld = d.vt_ld;
     a.seq = d.seq;
     a.heads = d.heads;
-    a.debug = d.debug;
     a.v_hd = d.v_head_dim > 0 ? d.v_head_dim : 128;
 
     // output tensor maps for the TMA-store epilogue (BN == 256): [32 rows x 64 columns] boxes, 128B swizzle

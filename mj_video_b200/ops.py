@@ -26,7 +26,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None, *, e
          bias=None, residual=None, scale=None, block_n: int = 0, out_k=None, out_vt=None, rope_cos=None,
          rope_sin=None, row_pos=None, row_map=None, row_vt=None, pos_emb=None, n_q_cols: int = 0, n_k_cols: int = 0,
          vt_stride_head: int = 0, vt_ld: int = 0, seq: int = 0, heads: int = 0, ldo: int | None = None,
-         K: int | None = None, debug: int = 0, cta_group: int = 0, v_head_dim: int = 0) -> torch.Tensor:
+         K: int | None = None, cta_group: int = 0, v_head_dim: int = 0) -> torch.Tensor:
     """D = A · Wᵀ with a fused epilogue (tcgen05 / TMEM / TMA). a: [M, K] bf16, w: [N, K] bf16 (nn.Linear layout)."""
     lib = _lib.load()
     _bf16(a, "a"), _bf16(w, "w")
@@ -54,7 +54,6 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None, *, e
     d.row_vt = _lib.ptr(row_vt)
     d.n_q_cols, d.n_k_cols = n_q_cols, n_k_cols
     d.vt_stride_head, d.vt_ld, d.seq, d.heads = vt_stride_head, vt_ld, seq, heads
-    d.debug = debug
     d.cta_group = cta_group
     d.v_head_dim = v_head_dim
     _lib.check(lib.mjv_gemm_bf16(C.byref(d), _lib.current_stream()))

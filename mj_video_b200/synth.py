@@ -129,7 +129,9 @@ def _norm(sd, g, prefix, n, bias=True):
 
 
 def make_state_dict(d: ModelDims, seed: int = 1234, include_lm_head: bool = True) -> dict[str, torch.Tensor]:
-    """fp32 CPU state dict with the reference's key space. Deterministic in (dims, seed)."""
+    """fp32 CPU state dict with the reference's key space. Deterministic in (dims, seed, include_lm_head):
+    the LM head draws from the same generator, so the projector / head tensors generated after it differ between the two
+    settings — compare a model only with one built from the SAME dict."""
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
     sd: dict[str, torch.Tensor] = {}

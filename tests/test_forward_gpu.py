@@ -491,3 +491,30 @@ def test_linear_rope_scaling(gpu):
     ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=25)])
     mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
     _check(mine, port.Oracle(d, sd, dtype=torch.float32, device=gpu).forward(pv.float(), ids, mask))
+
+
+def test_fp32_pixel_values_and_fp32_module(tiny_engine, gpu):
+    """pixel_values as the reference's `load_video` returns them (CPU-produced fp32, moved to the GPU without a cast) go
+    through the fp32 im2col path; an fp32 drop-in module returns fp32 tensors like the reference would."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from mj_video_b200.model import InternVLChatRewardModeling
+    d, sd, eng = tiny_engine
+    pv16 = load_video(synth.make_video(61), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)[0]
+    ids, mask = synth.pad_batch([synth.make_input_ids(4, [1] * 8, n_cap=31)])
+    a = eng.forward(pv16, ids, mask, synth.PAD, synth.IMG_CONTEXT)["scores"].clone()
+    b = eng.forward(pv16.float(), ids, mask, synth.PAD, synth.IMG_CONTEXT)["scores"].clone()
+    assert torch.equal(a, b)       # the same bf16-representable pixels, whichever container they arrive in
+    pv32 = load_video(synth.make_video(61), num_segments=8, max_num=1)[0]          # CPU fp32, unrounded
+    c = eng.forward(pv32.cuda(), ids, mask, synth.PAD, synth.IMG_CONTEXT)["scores"]
+    assert (c - a).abs().max().item() < 1e-2                                        # pixel rounding only
+    m = InternVLChatRewardModeling("unused", _tiny_cfg(d))
+    sd_full = dict(sd)     # the engine fixture's weights + the (unused) LM head the module's strict loading expects
+    sd_full["model.language_model.output.weight"] = torch.zeros(d.vocab, d.llm_hidden)
+    m.load_state_dict(sd_full, strict=True)
+    m.config.pad_token_id = synth.PAD
+    m = m.cuda().eval()                                                             # stays fp32
+    m.model.img_context_token_id = synth.IMG_CONTEXT
+    out = m.forward(pv32.cuda(), ids.cuda(), mask.cuda())
+    assert out.rewards.dtype == torch.float32 and out.hidden_state.dtype == torch.float32
+    assert (out.score.cpu() - c[:, -1].cpu()).abs().max().item() < 1e-3

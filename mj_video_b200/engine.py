@@ -11,7 +11,6 @@ Index semantics are the reference's:
 from __future__ import annotations
 
 import ctypes as C
-import math
 import warnings
 from dataclasses import dataclass
 

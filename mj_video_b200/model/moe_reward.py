@@ -14,7 +14,6 @@ import glob
 import os
 import weakref
 from collections import OrderedDict
-from dataclasses import dataclass, fields
 from typing import Optional
 
 import torch

@@ -518,3 +518,33 @@ def test_fp32_pixel_values_and_fp32_module(tiny_engine, gpu):
     out = m.forward(pv32.cuda(), ids.cuda(), mask.cuda())
     assert out.rewards.dtype == torch.float32 and out.hidden_state.dtype == torch.float32
     assert (out.score.cpu() - c[:, -1].cpu()).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_forward_fuzz_ragged_shapes(tiny_engine, gpu, seed):
+    """Randomised batches: 1-5 rows, 1-8 frames per row, clip geometries that tile into 1-5 tiles per frame, captions of
+    0-300 tokens, either prompt layout — against the fp32 oracle."""
+    import numpy as np
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from oracle import port
+    d, sd, eng = tiny_engine
+    rng = np.random.default_rng(1000 + seed)
+    geoms = [(448, 448, 1), (360, 640, 2), (300, 500, 4), (448, 448, 1), (500, 300, 4), (224, 224, 1)]
+    B = int(rng.integers(1, 6))
+    pvs, rows = [], []
+    for r in range(B):
+        H, W, mx = geoms[int(rng.integers(0, len(geoms)))]
+        nf = int(rng.integers(1, 9))
+        vid = synth.make_video(7000 + 10 * seed + r, n_frames=2 * nf, height=H, width=W)
+        pv, counts = load_video(vid, num_segments=nf, max_num=mx, device="cuda", dtype=torch.bfloat16)
+        ref_pv, ref_counts = port.load_video_frames(vid, num_segments=nf, max_num=mx)
+        assert counts == ref_counts and torch.equal(pv.float().cpu(), ref_pv.to(torch.bfloat16).float())
+        pvs.append(pv)
+        rows.append(synth.make_input_ids(seed * 10 + r, counts, n_cap=int(rng.integers(0, 301)),
+                                         first_slot_layout=bool(rng.integers(0, 2))))
+    pv = torch.cat(pvs)
+    ids, mask = synth.pad_batch(rows)
+    mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
+    ref = port.Oracle(d, sd, dtype=torch.float32, device=gpu).forward(pv.float(), ids, mask)
+    _check(mine, ref)

@@ -364,3 +364,68 @@ def test_attention_is_deterministic_under_stress(ops):
     torch.cuda.synchronize()
     assert not torch.isnan(outs[0].float()).any()
     assert all(torch.equal(outs[0], x) for x in outs[1:])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_gemm_fuzz_shapes(ops, seed):
+    """Random M (ragged), N (multiples of 128), K (multiples of 8) through the STORE and in-place RESID epilogues, both
+    tile widths where N allows."""
+    import random
+    rnd = random.Random(seed)
+    M = rnd.choice([1, 7, 127, 128, 129, 255, 257, 1000, 3333, 5001])
+    N = 128 * rnd.randint(1, 12)
+    K = 8 * rnd.randint(1, 300)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * (1.0 / math.sqrt(K))).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g).bfloat16()
+    ref = mm(a, w)
+    for bn in ([128, 256] if N % 256 == 0 else [128]):
+        close(ops.gemm(a, w, bias=bias, block_n=bn), (ref + bias.float()).bfloat16())
+        res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+        buf = res.clone()
+        ops.gemm(a, w, out=buf, residual=buf, epilogue=ops.EPI_RESID, block_n=bn)
+        close(buf, (res.float() + ref.bfloat16().float()).bfloat16())
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_attention_fuzz_lengths(ops, seed):
+    """Random ragged sequence sets around the 64 / 128 block boundaries, causal GQA (hd 128) and bidirectional (hd 64)."""
+    import random
+    rnd = random.Random(100 + seed)
+    lens = [rnd.choice([1, 2, 63, 64, 65, 127, 128, 129, 191, 192, 193, 500, 1025]) for _ in range(rnd.randint(1, 6))]
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    tot, H, Hkv = sum(lens), 4, 2
+    q = torch.randn(tot, H, 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(tot, Hkv, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(tot, Hkv, 128, device="cuda", generator=g).bfloat16()
+    starts, vt_cols = ops.vt_layout(lens)
+    vt = torch.zeros(Hkv, 128, vt_cols, device="cuda", dtype=torch.bfloat16)
+    o = 0
+    for st, n in zip(starts, lens):
+        vt[:, :, st:st + n] = v[o:o + n].permute(1, 2, 0)
+        o += n
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    out = torch.zeros(tot, H * 128, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q.reshape(tot, -1), k.reshape(tot, -1), vt, out, head_dim=128, heads=H, kv_heads=Hkv, causal=True,
+                  scale=1 / math.sqrt(128), cu_seqlens=cu, work=ops.causal_work_list(lens).cuda(),
+                  vt_starts=torch.tensor(starts, dtype=torch.int32, device="cuda"), vt_cols=vt_cols)
+    refs, o = [], 0
+    for n in lens:
+        refs.append(ref_attn(q[o:o + n].float(), k[o:o + n].float(), v[o:o + n].float(), True, 1 / math.sqrt(128)))
+        o += n
+    assert (out.float() - torch.cat(refs)).abs().max().item() < 2e-2
+    # bidirectional, fixed length per "tile"
+    S, T, Hh = rnd.choice([1, 64, 65, 200, 1025]), rnd.randint(1, 3), 2
+    Cv = Hh * 64
+    qb, kb, vb = [torch.randn(T * S, Hh, 64, device="cuda", generator=g).bfloat16() for _ in range(3)]
+    qk = torch.cat([qb.reshape(T * S, Cv), kb.reshape(T * S, Cv)], dim=1).contiguous()
+    S_pad = (S + 7) // 8 * 8
+    vtb = torch.zeros(T * Hh, 64, S_pad, device="cuda", dtype=torch.bfloat16)
+    vtb[:, :, :S] = vb.reshape(T, S, Hh, 64).permute(0, 2, 3, 1).reshape(T * Hh, 64, S)
+    outb = torch.zeros(T * S, Cv, device="cuda", dtype=torch.bfloat16)
+    ops.attention(qk, qk, vtb, outb, head_dim=64, heads=Hh, kv_heads=Hh, causal=False, scale=0.125, q_col0=0, k_col0=Cv,
+                  nseq=T, seq_len=S)
+    refb = torch.cat([ref_attn(qb.view(T, S, Hh, 64)[t].float(), kb.view(T, S, Hh, 64)[t].float(),
+                               vb.view(T, S, Hh, 64)[t].float(), False, 0.125) for t in range(T)])
+    assert (outb.float() - refb).abs().max().item() < 2e-2

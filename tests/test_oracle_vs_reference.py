@@ -44,6 +44,23 @@ def test_llama_branch_bit_exact(dtype):
         assert torch.equal(ref[k].float(), out[k].float()), k
 
 
+def test_forward_bit_exact_bf16():
+    """The reference's own `.to(bfloat16)` forward (what its GPU runs compute, here on the CPU): the oracle's bf16 mode
+    reproduces every rounding point — values AND output dtypes (bf16 tensors, fp32 aspect_scores / score: SURVEY §A.3)."""
+    from oracle import reference_harness as rh
+    d = synth.dims_tiny()
+    sd = synth.make_state_dict(d, seed=3)
+    m = rh.build_reference_model(d, sd, dtype=torch.bfloat16)
+    pv = torch.cat([rh.reference_load_video(synth.make_video(v), num_segments=8, max_num=1)[0] for v in (3, 4)]).to(torch.bfloat16)
+    ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=46), synth.make_input_ids(1, [1] * 8, n_cap=20)])
+    ref = rh.reference_forward(m, pv, ids, mask)
+    out = port.Oracle(d, sd, dtype=torch.bfloat16).forward(pv, ids, mask)
+    assert set(ref) == set(out)
+    for k in ref:
+        assert ref[k].dtype == out[k].dtype, k
+        assert torch.equal(ref[k].float(), out[k].float()), k
+
+
 def test_first_slot_layout(ref_model):
     """All IMG_CONTEXT tokens in the first <image> slot (what the reference's own callers produce)."""
     d, sd, m, rh = ref_model

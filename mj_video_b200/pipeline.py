@@ -60,7 +60,8 @@ class PairScorer:
     sampled frames of the clip, i.e. what `load_video` feeds to dynamic_preprocess) and prompt token ids."""
 
     def __init__(self, forward_fn, preprocess_fn, pad_token_id: int, rows_per_step: int = 32, max_num: int = 1,
-                 input_size: int = 448, device=None, group=None, prefetch: int = 2, gather_fn=None):
+                 input_size: int = 448, device=None, group=None, prefetch: int = 2, gather_fn=None,
+                 preprocess_batch_fn=None):
         """forward_fn(pixel_values, input_ids, attention_mask) -> [rows, W] fp32 score table on `device`;
         preprocess_fn(frames_u8_device, input_size, max_num) -> (tiles, tiles_per_frame)."""
         if rows_per_step < 2 or rows_per_step % 2:
@@ -73,6 +74,8 @@ class PairScorer:
         self.prefetch = max(1, prefetch)
         # (local table, n_pairs) -> full table; default: torch.distributed all-gather (gloo on CPU, NCCL on GPU)
         self.gather_fn = gather_fn or (lambda local, n: mdist.allgather_scores(local, n, group))
+        # optional: (list of device uint8 clips) -> all tiles of the micro-batch in ONE buffer (no per-row concat copy)
+        self.preprocess_batch_fn = preprocess_batch_fn
 
     @classmethod
     def for_engine(cls, engine, pad_token_id: int, img_context_token_id: int, **kw):
@@ -85,10 +88,26 @@ class PairScorer:
         def pre(frames_dev, input_size, max_num):
             return preprocess_frames(frames_dev, input_size, max_num, True, torch.bfloat16)
 
+        def pre_batch(clips, input_size, max_num):
+            """Tile counts are known on the host (grid choice, data.py:66-99), so every clip's tiles are written straight
+            into their slice of one micro-batch buffer."""
+            from .data_processor.data import find_closest_aspect_ratio
+            counts = []
+            for f in clips:
+                gi, gj = find_closest_aspect_ratio(f.shape[2], f.shape[1], 1, max_num, input_size)
+                counts.append(f.shape[0] * (gi * gj + (1 if gi * gj > 1 else 0)))
+            pv = torch.empty((sum(counts), 3, input_size, input_size), dtype=torch.bfloat16, device=engine.device)
+            off = 0
+            for f, n in zip(clips, counts):
+                preprocess_frames(f, input_size, max_num, True, torch.bfloat16, out=pv[off: off + n])
+                off += n
+            return pv
+
         import torch.distributed as tdist
         if "gather_fn" not in kw and tdist.is_available() and tdist.is_initialized() and \
                 tdist.get_world_size(kw.get("group")) > 1:
             kw["gather_fn"] = mdist.NcclScoreGather(engine.device, kw.get("group")).gather  # C ABI: mjv_allgather_scores
+        kw.setdefault("preprocess_batch_fn", pre_batch)
         return cls(fwd, pre, pad_token_id, device=engine.device, **kw)
 
     # ------------------------------------------------------------------------------------------------
@@ -123,13 +142,14 @@ class PairScorer:
             nxt = q.get()                                     # collated by the producer while the GPU was busy
             if cuda:
                 torch.cuda.current_stream(self.device).wait_event(ready)
-            tiles = []
-            for f in frames_dev:                              # per row: geometry may differ between clips
-                t, _ = self.preprocess_fn(f, self.input_size, self.max_num)
-                tiles.append(t)
-                if cuda:
+            if self.preprocess_batch_fn is not None:
+                pv = self.preprocess_batch_fn(frames_dev, self.input_size, self.max_num)
+            else:
+                tiles = [self.preprocess_fn(f, self.input_size, self.max_num)[0] for f in frames_dev]
+                pv = torch.cat(tiles) if len(tiles) > 1 else tiles[0]
+            if cuda:
+                for f in frames_dev:                          # clips were copied on the side stream
                     f.record_stream(torch.cuda.current_stream(self.device))
-            pv = torch.cat(tiles) if len(tiles) > 1 else tiles[0]
             scores = self.forward_fn(pv, hb.input_ids, hb.attention_mask).to(torch.float32)
             if local is None:
                 local = torch.zeros((2 * len(mine), scores.shape[1]), dtype=torch.float32, device=scores.device)

@@ -40,11 +40,25 @@ def prepare_chat_input(config, tokenizer, pixel_values, question, generation_con
         image_tokens = IMG_START_TOKEN + IMG_CONTEXT_TOKEN * num_image_token * num_patches + IMG_END_TOKEN
         query = query.replace('<image>', image_tokens, 1)
 
-    model_inputs = tokenizer(query, return_tensors='pt')
-    input_ids = model_inputs['input_ids'].to(device)
-    attention_mask = model_inputs['attention_mask'].to(device)
+    # The expanded prompt is ~30 KB of text for 8 frames; the chosen and the rejected row of a preference pair share it
+    # verbatim (same caption, same tile counts), so the tokenisation of the last few prompts is memoised per tokenizer
+    # (host-side caching only — same inputs, same ids; clones are returned).
+    key = (id(tokenizer), query)
+    hit = _TOKENIZED.get(key)
+    if hit is None:
+        model_inputs = tokenizer(query, return_tensors='pt')
+        hit = (model_inputs['input_ids'].clone(), model_inputs['attention_mask'].clone())
+        if len(_TOKENIZED) >= _TOKENIZED_MAX:
+            _TOKENIZED.pop(next(iter(_TOKENIZED)))
+        _TOKENIZED[key] = hit
+    input_ids = hit[0].clone().to(device)
+    attention_mask = hit[1].clone().to(device)
     generation_config['eos_token_id'] = eos_token_id
     return input_ids, attention_mask
+
+
+_TOKENIZED: dict = {}      # (id(tokenizer), prompt text) -> (input_ids, attention_mask), insertion-ordered, bounded
+_TOKENIZED_MAX = 32
 
 
 # ------------------------------------------------------------------------------------------------ parameter containers

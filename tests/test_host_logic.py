@@ -250,3 +250,39 @@ def test_opencv_reader_decodes_a_real_file(tmp_path):
     assert all(np.array_equal(got[k], allf[int(i)]) for k, i in enumerate(idx))
     assert np.abs(got[0].astype(int) - vid[int(idx[0])].astype(int)).mean() < 12     # MJPG is lossy but close
     assert isinstance(dp.open_video(path), (dp._OpenCVReader, dp._DecordReader, dp._AvReader))
+
+
+def test_prepare_chat_input_memoises_identical_prompts():
+    """Chosen and rejected rows of a pair share the prompt: the second call must not tokenise again, and must return
+    independent tensors with the same ids."""
+    import torch
+    from mj_video_b200.model import InternVLChatRewardModelingConfig, prepare_chat_input
+    from oracle.make_golden import StubTokenizer
+
+    class Counting(StubTokenizer):
+        calls = 0
+
+        def __call__(self, text, return_tensors="pt"):
+            Counting.calls += 1
+            return super().__call__(text, return_tensors)
+    d = synth.dims_tiny()
+    cfg = InternVLChatRewardModelingConfig(
+        vision_config=dict(hidden_size=d.vit_hidden, num_attention_heads=d.vit_heads, intermediate_size=d.vit_mlp,
+                           num_hidden_layers=d.vit_layers, image_size=448, patch_size=14),
+        llm_config=dict(architectures=["InternLM2ForCausalLM"], hidden_size=d.llm_hidden, intermediate_size=d.llm_inter,
+                        num_hidden_layers=d.llm_layers, num_attention_heads=d.llm_heads,
+                        num_key_value_heads=d.llm_kv_heads, vocab_size=d.vocab),
+        template="internlm2-chat", downsample_ratio=0.5, ps_version="v2", select_layer=-1, force_image_size=448,
+        num_objectives=28, num_aspects=5, aspect2criteria=d.aspect2criteria)
+    tok = Counting()
+    pv = torch.zeros(8, 3, 448, 448)
+    q = "".join(f"Frame{i+1}: <image>\n" for i in range(8)) + "a red kite"
+    a_ids, a_mask = prepare_chat_input(cfg, tok, pv, q, {}, num_patches_list=[1] * 8)
+    b_ids, b_mask = prepare_chat_input(cfg, tok, pv, q, {}, num_patches_list=[1] * 8)
+    assert Counting.calls == 1 and torch.equal(a_ids, b_ids) and torch.equal(a_mask, b_mask)
+    assert a_ids.data_ptr() != b_ids.data_ptr()
+    a_ids[0, 0] = -5                                   # callers may edit their tensors without poisoning the cache
+    c_ids, _ = prepare_chat_input(cfg, tok, pv, q, {}, num_patches_list=[1] * 8)
+    assert torch.equal(c_ids, b_ids)
+    prepare_chat_input(cfg, tok, pv, q + "!", {}, num_patches_list=[1] * 8)
+    assert Counting.calls == 2

@@ -7,6 +7,8 @@ in the CUDA library behind `InternVLChatRewardModeling.forward`.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 from torch import nn
 
@@ -45,9 +47,15 @@ def prepare_chat_input(config, tokenizer, pixel_values, question, generation_con
     # (host-side caching only — same inputs, same ids; clones are returned).
     key = (id(tokenizer), query)
     hit = _TOKENIZED.get(key)
+    if hit is not None and hit[2] is not None and hit[2]() is not tokenizer:
+        hit = None  # the id was recycled by another tokenizer object
     if hit is None:
         model_inputs = tokenizer(query, return_tensors='pt')
-        hit = (model_inputs['input_ids'].clone(), model_inputs['attention_mask'].clone())
+        try:
+            ref = weakref.ref(tokenizer)
+        except TypeError:
+            ref = None
+        hit = (model_inputs['input_ids'].clone(), model_inputs['attention_mask'].clone(), ref)
         if len(_TOKENIZED) >= _TOKENIZED_MAX:
             _TOKENIZED.pop(next(iter(_TOKENIZED)))
         _TOKENIZED[key] = hit

@@ -181,6 +181,18 @@ def test_compute_entry_points_fail_loudly_without_gpu(built_lib):
     assert b"no CUDA device" in built_lib.mjv_last_error()
 
 
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CUDA extension -> an error that says so; nothing falls back to PyTorch or the oracle."""
+    from mj_video_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "_LIB_PATH", tmp_path / "libmjv_b200.so")
+    with pytest.raises(_lib.MjvError, match="no CPU/PyTorch fallback"):
+        _lib.load()
+    from mj_video_b200 import ops
+    with pytest.raises(_lib.MjvError):
+        ops.gemm(torch.zeros(1, 8, dtype=torch.bfloat16), torch.zeros(128, 8, dtype=torch.bfloat16))
+
+
 def test_pair_sharding():
     from mj_video_b200.dist import pair_rows, preference_decisions, shard_pairs
     for n, w in [(4096, 8), (4096, 2), (10, 4), (3, 8), (0, 2)]:

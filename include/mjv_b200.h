@@ -39,6 +39,9 @@ enum {
 enum { MJV_DTYPE_F32 = 0, MJV_DTYPE_BF16 = 1, MJV_DTYPE_F16 = 2 };
 
 int mjv_abi_version(void);
+/* sizeof() of the ABI structs as this library was compiled (0 mjv_gemm_desc, 1 mjv_attn_desc, 2 mjv_config, 3 mjv_batch,
+ * 4 mjv_outputs; -1 otherwise): lets a binding check its own struct mirrors before the first compute call. */
+int mjv_abi_struct_size(int which);
 const char* mjv_last_error(void);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -96,6 +96,12 @@ def load() -> C.CDLL:
             "mj_video_b200 has no CPU/PyTorch fallback.")
     lib = C.CDLL(str(_LIB_PATH))
     lib.mjv_abi_version.restype = C.c_int
+    lib.mjv_abi_struct_size.argtypes = [C.c_int]
+    lib.mjv_abi_struct_size.restype = C.c_int
+    for which, mirror in enumerate((GemmDesc, AttnDesc, Config, Batch, Outputs)):
+        if lib.mjv_abi_struct_size(which) != C.sizeof(mirror):
+            raise MjvError(f"ABI mismatch: {mirror.__name__} is {C.sizeof(mirror)} bytes here but "
+                           f"{lib.mjv_abi_struct_size(which)} in {_LIB_PATH.name}; rebuild the library")
     lib.mjv_last_error.restype = C.c_char_p
     lib.mjv_launch_count.restype = C.c_longlong
     lib.mjv_reset_launch_count.restype = None

@@ -68,6 +68,16 @@ void profile_end(int slot, cudaStream_t st) {
 }  // namespace mjv
 
 extern "C" int mjv_abi_version(void) { return MJV_ABI_VERSION; }
+extern "C" int mjv_abi_struct_size(int which) {
+    switch (which) {
+        case 0: return static_cast<int>(sizeof(mjv_gemm_desc));
+        case 1: return static_cast<int>(sizeof(mjv_attn_desc));
+        case 2: return static_cast<int>(sizeof(mjv_config));
+        case 3: return static_cast<int>(sizeof(mjv_batch));
+        case 4: return static_cast<int>(sizeof(mjv_outputs));
+        default: return -1;
+    }
+}
 extern "C" const char* mjv_last_error(void) { return mjv::last_error_buf(); }
 extern "C" long long mjv_launch_count(void) { return mjv::launch_counter().load(); }
 extern "C" void mjv_reset_launch_count(void) { mjv::launch_counter().store(0); }

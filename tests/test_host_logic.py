@@ -147,6 +147,16 @@ def test_abi_exports_every_declared_symbol(built_lib):
     assert built_lib.mjv_abi_version() == 1
 
 
+def test_ctypes_mirrors_match_the_compiled_structs(built_lib):
+    """Every ctypes.Structure in _lib.py has the size (hence field layout up to padding) the C compiler gave the struct of
+    include/mjv_b200.h; _lib.load() itself refuses to continue otherwise."""
+    from mj_video_b200 import _lib
+    lib = _lib.load()
+    for which, mirror in enumerate((_lib.GemmDesc, _lib.AttnDesc, _lib.Config, _lib.Batch, _lib.Outputs)):
+        assert lib.mjv_abi_struct_size(which) == C.sizeof(mirror), mirror.__name__
+    assert lib.mjv_abi_struct_size(99) == -1
+
+
 def test_host_helpers_of_the_library(built_lib):
     """Pure-host entry points: grid choice and the Pillow coefficient tables equal the oracle's."""
     gi, gj = C.c_int32(), C.c_int32()

@@ -330,3 +330,22 @@ def test_product_never_imports_the_oracle_or_the_reference():
         assert "/root/reference" not in f.read_text(errors="ignore")
     bench = (pathlib.Path(ROOT) / "bench.py").read_text()
     assert "reference_harness" not in bench and "REFERENCE_ROOT" not in bench   # the GPU box has no reference tree
+
+
+def test_plain_c_host_links_against_the_abi(built_lib, tmp_path):
+    """include/mjv_b200.h is plain C and examples/abi_host.c — a non-Python caller — compiles, links against the shared
+    library and runs its host-only part (struct sizes, grid choice; mjv_create fails loudly without a GPU)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from mj_video_b200 import _lib
+    libdir = str(_lib.lib_path().parent)
+    exe = str(tmp_path / "abi_host")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c",
+                    os.path.join(ROOT, "include", "mjv_b200.h")], check=True)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "abi_host.c"),
+                    "-o", exe, "-L", libdir, "-lmjv_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "grid rc 0: 3 x 2" in res.stdout

@@ -1,0 +1,604 @@
+// Fused softmax attention, second generation: TWO 128-row query tiles per CTA, 128-column KV blocks, one CTA per SM.
+//
+// Replaces K6  flash_attn_varlen_qkvpacked_func(causal=False)  modeling_intern_vit.py:72-75 / _naive_attn :210-227
+//                        K15 flash_attn_func / flash_attn_varlen_func(causal=True) modeling_internlm2.py:498-561 / eager :393-410
+//
+// Why a second kernel (profiles/r01_ncu_full_attn_vit_v4.csv, source page): in attn_sm100.cuh a softmax warp spent only
+// 38 % of its time in the exponential loop; the rest was per-64-column-step overhead (barrier waits, spill reloads under
+// the 128-register cap of two CTAs per SM, instruction-cache misses of the doubly unrolled masked path, the item epilogue).
+// Here every step covers 128 columns, the two softmax warpgroups own 192 registers per thread (setmaxnreg), the masked
+// path is a small pre-pass in front of the one exponential loop, and the O / l -> bf16 epilogue runs on its own
+// warpgroup while the softmax warps already work on the next item.
+//
+// Roles (512 threads, 16 warps; TMEM lane quarter of a warp = warp % 4):
+//   warps 0-3   softmax of query tile 0 (thread = one query row, 128 scores per step)
+//   warps 4-7   softmax of query tile 1
+//   warps 8-11  epilogue: O_t / l -> bf16 -> global, then hands the accumulator back (o_empty)
+//   warp  12    TMA producer (Q tiles, K ring, V^T ring)
+//   warp  13    MMA issuer (S = Q·K^T into a ring of kNSB score buffers; O_t += P·V with P read from TMEM)
+// The two query tiles of an item share every K / V^T tile (one smem read stream for both):
+//   * bidirectional batched mode (ViT): consecutive 128-row blocks of one (sequence, head);
+//   * causal varlen mode with an even GQA group (InternLM2, 16 q / 8 kv heads): the two query heads of one kv head at the
+//     same query block - identical masks, shared K/V;
+//   * causal varlen mode otherwise (MHA, e.g. the Llama / Phi-3 shaped branch): two query blocks of one head, packed by the
+//     host in one work entry (low 16 bits: first block, high 16 bits: second block + 1, or 0 for none).
+// Steps are numbered globally (g) in the order (block j, tile t) over the active tiles; step g uses score buffer
+// g % kNSB. tcgen05.mma executes in issue order, so S_{g+kNSB} (same buffer) is issued right after P_g·V and cannot
+// overwrite P_g early. The running maximum is updated lazily (only when it grows by more than 2^8), the rare rescale of
+// O_t happens in the softmax warps after waiting for the previous P·V of that tile (pv_done).
+#pragma once
+#include "attn_sm100.cuh"
+
+namespace mjv {
+namespace attn2 {
+
+constexpr int BQ = 128;
+constexpr int BKV = 128;
+constexpr int kThreads = 512;
+constexpr int kNSB = 2;
+constexpr float kRescaleThreshold = 8.0f;  // log2 domain: p stays below 2^8
+
+template <int HD>
+struct Smem {
+    static constexpr int kQSets = HD == 64 ? 2 : 1;    // item-level double buffering of the Q tile pair
+    static constexpr int kQBufs = 2 * kQSets;
+    static constexpr int kKStages = HD == 64 ? 3 : 2;
+    static constexpr int kVStages = HD == 64 ? 3 : 2;
+    static constexpr int kQBytes = BQ * HD * 2;
+    static constexpr int kKBytes = BKV * HD * 2;
+    static constexpr int kVBytes = HD * BKV * 2;
+    static constexpr int kQOff = 0;
+    static constexpr int kKOff = kQOff + kQBufs * kQBytes;
+    static constexpr int kVOff = kKOff + kKStages * kKBytes;
+    static constexpr int kLOff = kVOff + kVStages * kVBytes;  // row sums handed to the epilogue: [2][128] fp32
+    static constexpr int kBarOff = kLOff + 2 * BQ * 4;
+    static constexpr int kTotal = kBarOff + 512;
+};
+
+// two-element fields are only ever indexed with compile-time constants (a runtime index would put them in local memory);
+// sel2() picks by a runtime tile number
+struct Item {
+    int row_base, len, tma_row0, tma_batch, kvh, v_plane, v_col0, nblk_max;
+    int h[2], q0[2], kv_end[2], nblk[2];
+};
+__device__ __forceinline__ int sel2(int t, const int* a) { return t != 0 ? a[1] : a[0]; }
+__device__ __forceinline__ uint32_t sel2(int t, const uint32_t* a) { return t != 0 ? a[1] : a[0]; }
+
+template <bool CAUSAL>
+__device__ __forceinline__ Item decode_item(const AttnArgs& a, int it) {
+    Item t;
+    int seq, qb0, qb1;
+    bool has1;
+    if (a.work != nullptr) {
+        if (a.pair_heads) {
+            const int per = a.heads >> 1;
+            const int2 w = a.work[it / per];
+            const int hp = it % per;
+            seq = w.x;
+            qb0 = qb1 = w.y & 0xffff;
+            has1 = true;
+            t.h[0] = 2 * hp;
+            t.h[1] = 2 * hp + 1;
+        } else {
+            const int2 w = a.work[it / a.heads];
+            seq = w.x;
+            qb0 = w.y & 0xffff;
+            const int hi = (w.y >> 16) & 0xffff;
+            has1 = hi != 0;
+            qb1 = hi - 1;
+            t.h[0] = t.h[1] = it % a.heads;
+        }
+    } else {
+        const int npairs = (a.n_qblocks + 1) >> 1;
+        const int pr = it % npairs;
+        const int sh = it / npairs;
+        t.h[0] = t.h[1] = sh % a.heads;
+        seq = sh / a.heads;
+        qb0 = 2 * pr;
+        qb1 = qb0 + 1;
+        has1 = qb1 < a.n_qblocks;
+    }
+    if (a.cu_seqlens != nullptr) {
+        t.row_base = a.cu_seqlens[seq];
+        t.len = a.cu_seqlens[seq + 1] - t.row_base;
+    } else {
+        t.len = a.seq_len;
+        t.row_base = seq * t.len;
+    }
+    t.q0[0] = qb0 * BQ;
+    t.q0[1] = qb1 * BQ;
+    t.kv_end[0] = CAUSAL ? min(t.len, t.q0[0] + BQ) : t.len;
+    t.kv_end[1] = CAUSAL ? min(t.len, t.q0[1] + BQ) : t.len;
+    t.nblk[0] = (t.kv_end[0] + BKV - 1) / BKV;
+    t.nblk[1] = has1 ? (t.kv_end[1] + BKV - 1) / BKV : 0;
+    t.nblk_max = max(t.nblk[0], t.nblk[1]);
+    t.tma_row0 = a.batched ? 0 : t.row_base;
+    t.tma_batch = a.batched ? seq : 0;
+    t.kvh = t.h[0] / a.kv_group;
+    t.v_plane = a.batched ? seq * a.heads + t.h[0] : t.kvh;
+    t.v_col0 = a.batched ? 0 : (a.vt_starts != nullptr ? a.vt_starts[seq] : t.row_base);
+    return t;
+}
+
+// what the MMA issuer needs of an item (it tracks two items at once: the S stream runs ahead of the P·V stream)
+struct ItemLite {
+    int nblk[2], kv_end[2], nblk_max;
+};
+template <bool CAUSAL>
+__device__ __forceinline__ ItemLite decode_lite(const AttnArgs& a, int it) {
+    const Item t = decode_item<CAUSAL>(a, it);
+    ItemLite l;
+    l.nblk[0] = t.nblk[0];
+    l.nblk[1] = t.nblk[1];
+    l.kv_end[0] = t.kv_end[0];
+    l.kv_end[1] = t.kv_end[1];
+    l.nblk_max = t.nblk_max;
+    return l;
+}
+
+// ---- softmax building blocks (C = 32-column chunk index, compile time; v = the 128 scores of this thread's row)
+template <int C>
+__device__ __forceinline__ void mask_chunk(uint32_t* v, int lim) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (C * 32 + i >= lim) v[C * 32 + i] = 0xff800000u;  // -inf
+}
+template <int C>
+__device__ __forceinline__ void max_chunk(const uint32_t* v, float* mx) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(v[C * 32 + i]), __uint_as_float(v[C * 32 + i + 1])));
+        mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(v[C * 32 + i + 2]), __uint_as_float(v[C * 32 + i + 3])));
+        mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(v[C * 32 + i + 4]), __uint_as_float(v[C * 32 + i + 5])));
+        mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(v[C * 32 + i + 6]), __uint_as_float(v[C * 32 + i + 7])));
+    }
+}
+// p = exp2(s*c - m) for the 32 scores of chunk C; packed bf16 pairs go to pk[16]; row-sum partials in ps2[4]
+template <int C>
+__device__ __forceinline__ void exp_chunk(const uint32_t* v, uint32_t* pk, uint64_t sc2, uint64_t nm2, uint64_t* ps2) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint64_t t2 = ptx::ffma2(
+            ptx::pack_f32x2(__uint_as_float(v[C * 32 + 2 * i]), __uint_as_float(v[C * 32 + 2 * i + 1])), sc2, nm2);
+        float t0, t1;
+        ptx::unpack_f32x2(t2, t0, t1);
+        const float p0 = ptx::ex2_approx(t0);
+        const float p1 = ptx::ex2_approx(t1);
+        ps2[i & 3] = ptx::fadd2(ps2[i & 3], ptx::pack_f32x2(p0, p1));
+        pk[i] = ptx::pack_bf16x2(p0, p1);
+    }
+}
+
+}  // namespace attn2
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(attn2::kThreads, 1)
+attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttnArgs args) {
+    using namespace attn2;
+    using L = Smem<HD>;
+    constexpr int KS = L::kKStages;
+    constexpr int VS = L::kVStages;
+    constexpr int QSETS = L::kQSets;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem + L::kQOff;
+    uint8_t* sK = smem + L::kKOff;
+    uint8_t* sV = smem + L::kVOff;
+    float* sL = reinterpret_cast<float*>(smem + L::kLOff);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    uint64_t* q_full = bars;                 // [4]
+    uint64_t* q_empty = bars + 4;            // [4]  Q tile consumed by the last S MMA of its item
+    uint64_t* k_full = bars + 8;             // [KS]
+    uint64_t* k_empty = k_full + KS;         // [KS] K tile consumed by the S MMAs of both query tiles
+    uint64_t* v_full = k_empty + KS;         // [VS]
+    uint64_t* v_empty = v_full + VS;         // [VS] V tile consumed by the P·V MMAs of both query tiles
+    uint64_t* s_full = v_empty + VS;         // [kNSB] scores ready (MMA -> softmax)
+    uint64_t* p_full = s_full + kNSB;        // [kNSB] probabilities written (softmax -> MMA), 4 warp arrivals
+    uint64_t* pv_done = p_full + kNSB;       // [2] every P·V of tile t (only waited on by the rare rescale)
+    uint64_t* o_done = pv_done + 2;          // [2] accumulator of tile t complete (MMA -> epilogue)
+    uint64_t* o_empty = o_done + 2;          // [2] accumulator read out (epilogue -> MMA / softmax), 4 warp arrivals
+    uint64_t* l_ready = o_empty + 2;         // [2] row sums in smem (softmax -> epilogue), 4 warp arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_ready + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_items = args.n_items;
+
+    if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need a 1024-byte aligned base
+    if (warp == 12 && lane == 0) {
+        ptx::prefetch_tmap(&tmQ);
+        ptx::prefetch_tmap(&tmK);
+        ptx::prefetch_tmap(&tmV);
+    }
+    if (warp == 13 && lane == 0) {
+        for (int b = 0; b < 4; ++b) {
+            ptx::mbar_init(&q_full[b], 1);
+            ptx::mbar_init(&q_empty[b], 1);
+        }
+        for (int s = 0; s < KS; ++s) {
+            ptx::mbar_init(&k_full[s], 1);
+            ptx::mbar_init(&k_empty[s], 1);
+        }
+        for (int s = 0; s < VS; ++s) {
+            ptx::mbar_init(&v_full[s], 1);
+            ptx::mbar_init(&v_empty[s], 1);
+        }
+        for (int b = 0; b < kNSB; ++b) {
+            ptx::mbar_init(&s_full[b], 1);
+            ptx::mbar_init(&p_full[b], 4);
+        }
+        for (int t = 0; t < 2; ++t) {
+            ptx::mbar_init(&pv_done[t], 1);
+            ptx::mbar_init(&o_done[t], 1);
+            ptx::mbar_init(&o_empty[t], 4);
+            ptx::mbar_init(&l_ready[t], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 14) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_O0 = tmem_base + kNSB * BKV;  // O_t at columns kNSB*128 + t*HD
+
+    const int wg = warp >> 2;
+    if (wg < 2) {
+        // ===================================================== softmax of query tile `wg` (TMEM lane == query row)
+        ptx::setmaxnreg_inc<192>();
+        const int tt = wg;
+        const int qw = warp & 3;
+        const int r = qw * 32 + lane;
+        const uint32_t lane_sel = static_cast<uint32_t>(qw * 32) << 16;
+        const uint32_t tmem_O = tmem_O0 + tt * HD + lane_sel;
+        int sb = 0;           // score buffer of the next step (ring over ALL active steps of both tiles)
+        uint32_t sph = 0;
+        uint32_t n_mine = 0;  // steps of this tile so far (global): pv_done[tt] has completed n_mine times when P·V caught up
+        uint32_t n_use = 0;   // items in which this tile was active so far
+        const float scale_log2 = args.scale_log2;
+
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const Item t = decode_item<CAUSAL>(args, it);
+            const int q0 = sel2(tt, t.q0), len = t.len, kv_end = sel2(tt, t.kv_end);
+            const int my_nblk = sel2(tt, t.nblk);
+            const int other_nblk = sel2(tt ^ 1, t.nblk);
+            const int qrow = q0 + r;
+            const bool warp_has_rows = (q0 + qw * 32) < len;  // warp-uniform
+            float m_run = -INFINITY;
+            float l_run = 0.0f;
+
+            for (int j = 0; j < t.nblk_max; ++j) {
+                if (tt == 1 && j < other_nblk) {  // tile 0's step of this block comes first in the ring
+                    // mbarrier waits only know a phase parity: a warpgroup that owns no step in this block must still
+                    // OBSERVE the foreign step's completion, or it runs ahead (e.g. through a whole single-tile item) and
+                    // its next own wait is satisfied by a completion two phases too early
+                    if (!(j < my_nblk)) ptx::mbar_wait_nocall(&s_full[sb], sph);
+                    if (++sb == kNSB) { sb = 0; sph ^= 1; }
+                }
+                if (j < my_nblk) {
+                    ptx::mbar_wait_nocall(&s_full[sb], sph);
+                    ptx::tc_fence_after();
+                    const uint32_t tmem_S = tmem_base + sb * BKV + lane_sel;
+                    const int kv0 = j * BKV;
+                    const int valid = min(BKV, kv_end - kv0);                    // columns of this block that exist
+                    const int lim = CAUSAL ? min(valid, qrow - kv0 + 1) : valid;  // per-row visible columns
+                    // columns at or beyond wlim are invisible to every row of this warp (warp-uniform)
+                    const int wlim = CAUSAL ? min(valid, q0 + qw * 32 + 32 - kv0) : valid;
+                    const bool full = (valid == BKV) && (!CAUSAL || (kv0 + BKV - 1 <= q0 + qw * 32));
+                    const int nch = (wlim + 31) >> 5;                  // 32-column chunks with visible columns
+                    const int pch = (((valid + 15) >> 4) + 1) >> 1;     // chunks the P·V MMA reads (16-column k-steps)
+                    if (warp_has_rows) {
+                        uint32_t v[128];
+                        ptx::tmem_ld_x32(tmem_S, v);
+                        if (nch > 1) ptx::tmem_ld_x32(tmem_S + 32, v + 32);
+                        if (nch > 2) ptx::tmem_ld_x32(tmem_S + 64, v + 64);
+                        if (nch > 3) ptx::tmem_ld_x32(tmem_S + 96, v + 96);
+                        ptx::tmem_wait_ld();
+                        if (!full) {
+                            mask_chunk<0>(v, lim);
+                            if (nch > 1) mask_chunk<1>(v, lim);
+                            if (nch > 2) mask_chunk<2>(v, lim);
+                            if (nch > 3) mask_chunk<3>(v, lim);
+                        }
+                        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                        max_chunk<0>(v, mx);
+                        if (nch > 1) max_chunk<1>(v, mx);
+                        if (nch > 2) max_chunk<2>(v, mx);
+                        if (nch > 3) max_chunk<3>(v, mx);
+                        const float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2;  // scale > 0
+                        // ---- lazy rescale of the TMEM accumulator
+                        float alpha = 1.0f;
+                        bool need = false;
+                        if (j == 0) {
+                            m_run = bm;
+                        } else if (bm > m_run + kRescaleThreshold) {
+                            alpha = ptx::ex2_approx(m_run - bm);
+                            m_run = bm;
+                            need = true;
+                        }
+                        if (__any_sync(0xffffffffu, need)) {
+                            // the previous P·V of this tile must have landed in O_t: completion number n_mine of pv_done[tt]
+                            ptx::mbar_wait_nocall(&pv_done[tt], (n_mine - 1) & 1);
+                            ptx::tc_fence_after();
+                            l_run *= alpha;
+#pragma unroll 1
+                            for (int c = 0; c < HD / 8; ++c) {
+                                uint32_t o[8];
+                                ptx::tmem_ld_x8(tmem_O + c * 8, o);
+                                ptx::tmem_wait_ld();
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                                ptx::tmem_st_x8(tmem_O + c * 8, o);
+                            }
+                            ptx::tmem_wait_st();
+                        }
+                        // ---- p = exp2(s*c - m), row sum, bf16 pack; P (bf16 pairs) overwrites the first 64 columns of S
+                        const uint64_t sc2 = ptx::pack_f32x2(scale_log2, scale_log2);
+                        const uint64_t nm2 = ptx::pack_f32x2(-m_run, -m_run);
+                        uint64_t ps2[4];
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) ps2[a] = ptx::pack_f32x2(0.f, 0.f);
+                        uint32_t pk[16];
+                        uint32_t zero16[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) zero16[i] = 0u;
+                        exp_chunk<0>(v, pk, sc2, nm2, ps2);
+                        ptx::tmem_st_x16(tmem_S, pk);
+                        if (nch > 1) {
+                            exp_chunk<1>(v, pk, sc2, nm2, ps2);
+                            ptx::tmem_st_x16(tmem_S + 16, pk);
+                        } else if (pch > 1) {
+                            ptx::tmem_st_x16(tmem_S + 16, zero16);
+                        }
+                        if (nch > 2) {
+                            exp_chunk<2>(v, pk, sc2, nm2, ps2);
+                            ptx::tmem_st_x16(tmem_S + 32, pk);
+                        } else if (pch > 2) {
+                            ptx::tmem_st_x16(tmem_S + 32, zero16);
+                        }
+                        if (nch > 3) {
+                            exp_chunk<3>(v, pk, sc2, nm2, ps2);
+                            ptx::tmem_st_x16(tmem_S + 48, pk);
+                        } else if (pch > 3) {
+                            ptx::tmem_st_x16(tmem_S + 48, zero16);
+                        }
+                        float s0, s1, s2, s3;
+                        ptx::unpack_f32x2(ptx::fadd2(ps2[0], ps2[1]), s0, s1);
+                        ptx::unpack_f32x2(ptx::fadd2(ps2[2], ps2[3]), s2, s3);
+                        l_run += (s0 + s1) + (s2 + s3);
+                        ptx::tmem_wait_st();
+                    }
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    // A warp without rows still waits for s_full above, so it can run at most kNSB-1 steps ahead of the
+                    // slowest warp: its early arrivals land on the other buffer's barrier, never in a phase too early.
+                    if (lane == 0) ptx::mbar_arrive(&p_full[sb]);
+                    ++n_mine;
+                    if (++sb == kNSB) { sb = 0; sph ^= 1; }
+                }
+                if (tt == 0 && j < other_nblk) {  // tile 1's step of this block follows in the ring
+                    if (!(j < my_nblk)) ptx::mbar_wait_nocall(&s_full[sb], sph);
+                    if (++sb == kNSB) { sb = 0; sph ^= 1; }
+                }
+            }
+            if (my_nblk > 0) {
+                // hand the row sums to the epilogue warpgroup (which must be done with the previous item's)
+                if (n_use > 0) ptx::mbar_wait_nocall(&o_empty[tt], (n_use - 1) & 1);
+                sL[tt * BQ + r] = l_run;
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&l_ready[tt]);
+                ++n_use;
+            }
+        }
+    } else if (wg == 2) {
+        // ===================================================== epilogue: O_t / l -> bf16 -> global
+        ptx::setmaxnreg_dec<80>();
+        const int qw = warp & 3;
+        const int r = qw * 32 + lane;
+        const uint32_t lane_sel = static_cast<uint32_t>(qw * 32) << 16;
+        uint32_t n_use[2] = {0, 0};
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const Item t = decode_item<CAUSAL>(args, it);
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt) {
+                if (t.nblk[tt] == 0) continue;
+                ptx::mbar_wait_nocall(&l_ready[tt], n_use[tt] & 1);
+                ptx::mbar_wait_nocall(&o_done[tt], n_use[tt] & 1);
+                ptx::tc_fence_after();
+                const int qrow = t.q0[tt] + r;
+                const bool warp_has_rows = (t.q0[tt] + qw * 32) < t.len;
+                if (warp_has_rows) {
+                    const float inv = 1.0f / sL[tt * BQ + r];
+                    __nv_bfloat16* dst =
+                        args.out + static_cast<long long>(t.row_base + qrow) * args.ldo + t.h[tt] * args.out_hd;
+                    const uint32_t tmem_O = tmem_O0 + tt * HD + lane_sel;
+#pragma unroll 1
+                    for (int c = 0; c < HD / 32; ++c) {
+                        if (c * 32 >= args.out_hd) break;  // columns beyond the model's head_dim are exact zeros: not stored
+                        uint32_t o[32];
+                        ptx::tmem_ld_x32(tmem_O + c * 32, o);
+                        ptx::tmem_wait_ld();
+                        if (qrow < t.len) {
+                            uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+                            for (int gq = 0; gq < 4; ++gq) {
+                                d4[gq] = make_uint4(
+                                    ptx::pack_bf16x2(__uint_as_float(o[8 * gq + 0]) * inv, __uint_as_float(o[8 * gq + 1]) * inv),
+                                    ptx::pack_bf16x2(__uint_as_float(o[8 * gq + 2]) * inv, __uint_as_float(o[8 * gq + 3]) * inv),
+                                    ptx::pack_bf16x2(__uint_as_float(o[8 * gq + 4]) * inv, __uint_as_float(o[8 * gq + 5]) * inv),
+                                    ptx::pack_bf16x2(__uint_as_float(o[8 * gq + 6]) * inv, __uint_as_float(o[8 * gq + 7]) * inv));
+                            }
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&o_empty[tt]);
+                ++n_use[tt];
+            }
+        }
+    } else {
+        ptx::setmaxnreg_dec<48>();
+        if (warp == 12) {
+            // ===================================================== TMA producer
+            if (ptx::elect_one()) {
+                int kst = 0, vst = 0;
+                uint32_t kph = 0, vph = 0;
+                uint32_t n_use[2] = {0, 0};
+                for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                    const Item t = decode_item<CAUSAL>(args, it);
+#pragma unroll
+                    for (int tt = 0; tt < 2; ++tt) {
+                        if (t.nblk[tt] == 0) continue;
+                        const int buf = (n_use[tt] % QSETS) * 2 + tt;
+                        ptx::mbar_wait_nocall(&q_empty[buf], ((n_use[tt] / QSETS) & 1) ^ 1);
+                        ptx::mbar_expect_tx(&q_full[buf], L::kQBytes);
+#pragma unroll
+                        for (int kd = 0; kd < HD / 64; ++kd)
+                            ptx::tma_load_3d(sQ + buf * L::kQBytes + kd * (BQ * 128), &tmQ, &q_full[buf],
+                                             args.q_col0 + t.h[tt] * HD + kd * 64, t.tma_row0 + t.q0[tt], t.tma_batch,
+                                             ptx::kEvictFirst);
+                        ++n_use[tt];
+                    }
+                    for (int j = 0; j < t.nblk_max; ++j) {
+                        ptx::mbar_wait_nocall(&k_empty[kst], kph ^ 1);
+                        ptx::mbar_expect_tx(&k_full[kst], L::kKBytes);
+#pragma unroll
+                        for (int kd = 0; kd < HD / 64; ++kd)
+                            ptx::tma_load_3d(sK + kst * L::kKBytes + kd * (BKV * 128), &tmK, &k_full[kst],
+                                             args.k_col0 + t.kvh * HD + kd * 64, t.tma_row0 + j * BKV, t.tma_batch,
+                                             ptx::kEvictLast);
+                        if (++kst == KS) { kst = 0; kph ^= 1; }
+                        ptx::mbar_wait_nocall(&v_empty[vst], vph ^ 1);
+                        ptx::mbar_expect_tx(&v_full[vst], L::kVBytes);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half)
+                            ptx::tma_load_3d(sV + vst * L::kVBytes + half * (HD * 128), &tmV, &v_full[vst],
+                                             t.v_col0 + j * BKV + half * 64, 0, t.v_plane, ptx::kEvictLast);
+                        if (++vst == VS) { vst = 0; vph ^= 1; }
+                    }
+                }
+            }
+        } else if (warp == 13) {
+            // ===================================================== MMA issuer
+            if (ptx::elect_one()) {
+                constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
+                constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD);
+                // ---- S stream: runs ahead of the P·V stream by up to kNSB steps, across item boundaries
+                int s_it = blockIdx.x;
+                bool s_done = s_it >= n_items;
+                ItemLite si;
+                si.nblk[0] = si.nblk[1] = si.kv_end[0] = si.kv_end[1] = si.nblk_max = 0;
+                if (!s_done) si = decode_lite<CAUSAL>(args, s_it);
+                int s_j = 0, s_t = 0;     // next S step (tile 0 is active in block 0 of every item)
+                int s_kst = 0;
+                uint32_t s_kph = 0;
+                uint32_t s_use[2] = {0, 0};
+                int gs = 0;               // S steps issued so far
+                auto issue_next_s = [&]() {
+                    const int t = s_t, j = s_j;
+                    const uint32_t use = sel2(t, s_use);
+                    const int buf = (use % QSETS) * 2 + t;
+                    if (j == 0) ptx::mbar_wait_nocall(&q_full[buf], (use / QSETS) & 1);
+                    const bool first_of_block = (t == 0) || !(j < si.nblk[0]);
+                    const bool last_of_block = (t == 1) || !(j < si.nblk[1]);
+                    if (first_of_block) ptx::mbar_wait_nocall(&k_full[s_kst], s_kph);
+                    ptx::tc_fence_after();
+                    const uint32_t q_addr = ptx::smem_u32(sQ + buf * L::kQBytes);
+                    const uint32_t k_addr = ptx::smem_u32(sK + s_kst * L::kKBytes);
+                    const uint32_t d = tmem_base + (gs % kNSB) * BKV;
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks) {
+                        const uint64_t a = ptx::make_desc_sw128(q_addr + (ks >> 2) * (BQ * 128) + (ks & 3) * 32);
+                        const uint64_t b = ptx::make_desc_sw128(k_addr + (ks >> 2) * (BKV * 128) + (ks & 3) * 32);
+                        ptx::mma_bf16_ss(d, a, b, idesc_s, ks != 0 ? 1u : 0u);
+                    }
+                    ptx::mma_commit(&s_full[gs % kNSB]);
+                    if (last_of_block) {
+                        ptx::mma_commit(&k_empty[s_kst]);  // K tile free once the S MMAs of both tiles retire
+                        if (++s_kst == KS) { s_kst = 0; s_kph ^= 1; }
+                    }
+                    if (j == sel2(t, si.nblk) - 1) {  // last S of this tile in the item: its Q tile can be replaced
+                        ptx::mma_commit(&q_empty[buf]);
+                        if (t != 0) ++s_use[1];
+                        else ++s_use[0];
+                    }
+                    ++gs;
+                    // advance to the next active step
+                    for (;;) {
+                        if (s_t == 0) {
+                            s_t = 1;
+                        } else {
+                            s_t = 0;
+                            ++s_j;
+                        }
+                        if (s_j >= si.nblk_max) {
+                            s_it += gridDim.x;
+                            if (s_it >= n_items) {
+                                s_done = true;
+                                return;
+                            }
+                            si = decode_lite<CAUSAL>(args, s_it);
+                            s_j = 0;
+                            s_t = 0;
+                        }
+                        if (s_j < sel2(s_t, si.nblk)) return;
+                    }
+                };
+                // ---- P·V stream
+                int vst = 0;
+                uint32_t vph = 0;
+                int g = 0;
+                uint32_t o_use[2] = {0, 0};
+                for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                    const ItemLite t = decode_lite<CAUSAL>(args, it);
+                    for (int j = 0; j < t.nblk_max; ++j) {
+                        const uint32_t v_addr = ptx::smem_u32(sV + vst * L::kVBytes);
+#pragma unroll
+                        for (int tt = 0; tt < 2; ++tt) {
+                            if (!(j < t.nblk[tt])) continue;
+                            while (gs < g + kNSB && !s_done) issue_next_s();
+                            ptx::mbar_wait_nocall(&p_full[g % kNSB], (g / kNSB) & 1);
+                            const bool first_of_block = (tt == 0) || !(j < t.nblk[0]);
+                            const bool last_of_block = (tt == 1) || !(j < t.nblk[1]);
+                            if (first_of_block) ptx::mbar_wait_nocall(&v_full[vst], vph);
+                            // the epilogue has read out the previous item's accumulator of this tile
+                            if (j == 0 && o_use[tt] > 0) ptx::mbar_wait_nocall(&o_empty[tt], (o_use[tt] - 1) & 1);
+                            ptx::tc_fence_after();
+                            const int valid = min(BKV, t.kv_end[tt] - j * BKV);
+                            const int ksteps = (valid + 15) >> 4;
+                            const uint32_t p_tmem = tmem_base + (g % kNSB) * BKV;  // P_g: bf16 pairs in the first 64 columns
+                            const uint32_t o_tmem = tmem_O0 + tt * HD;
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                const uint64_t b = ptx::make_desc_sw128(v_addr + (ks >> 2) * (HD * 128) + (ks & 3) * 32);
+                                ptx::mma_bf16_ts(o_tmem, p_tmem + ks * 8, b, idesc_o, (j | ks) != 0 ? 1u : 0u);
+                            }
+                            ptx::mma_commit(&pv_done[tt]);
+                            if (j == t.nblk[tt] - 1) {
+                                ptx::mma_commit(&o_done[tt]);
+                                ++o_use[tt];
+                            }
+                            if (last_of_block) {
+                                ptx::mma_commit(&v_empty[vst]);
+                                if (++vst == VS) { vst = 0; vph ^= 1; }
+                            }
+                            ++g;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 14) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace mjv

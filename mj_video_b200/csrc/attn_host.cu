@@ -1,6 +1,7 @@
 // Host launcher for the tcgen05 attention kernels (see attn_sm100.cuh).
-#include "attn_sm100.cuh"
+#include "attn2_sm100.cuh"
 #include "common.cuh"
+#include <stdlib.h>
 #include "launch.cuh"
 
 namespace mjv {
@@ -24,6 +25,31 @@ static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
     return 0;
 }
 
+template <int HD, bool CAUSAL>
+static int launch_attn2_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& a,
+                          dim3 grid, cudaStream_t stream, double work) {
+    using L = attn2::Smem<HD>;
+    auto kfn = attention2_kernel<HD, CAUSAL>;
+    static bool configured = false;
+    if (!configured) {
+        MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        configured = true;
+    }
+    {
+        LaunchScope scope(CAUSAL ? TAG_ATTN_CAUSAL : TAG_ATTN_BIDIR, stream, work);
+        kfn<<<grid, attn2::kThreads, L::kTotal, stream>>>(tq, tk, tv, a);
+    }
+    MJV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// MJV_ATTN_IMPL=1 selects the first-generation kernel (attn_sm100.cuh: one 128-row tile per CTA, 64-column blocks, two
+// CTAs per SM) for A/B measurements; the default is attention2_kernel (attn2_sm100.cuh).
+static int attn_impl() {
+    const char* e = getenv("MJV_ATTN_IMPL");  // read per call so that one process can time both
+    return (e != nullptr && e[0] == '1') ? 1 : 2;
+}
+
 int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     MJV_CHECK(d.head_dim == 64 || d.head_dim == 128, MJV_ERR_ARG, "attention: head_dim %d unsupported", d.head_dim);
     MJV_CHECK(d.heads > 0 && d.kv_heads > 0 && d.heads % d.kv_heads == 0, MJV_ERR_ARG, "attention: bad head counts");
@@ -31,7 +57,8 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     if (varlen) MJV_CHECK(d.work != nullptr && d.n_work > 0, MJV_ERR_ARG, "attention: varlen mode needs a work list");
     else MJV_CHECK(d.nseq > 0 && d.seq_len > 0, MJV_ERR_ARG, "attention: batched mode needs nseq/seq_len");
     const int hd = d.head_dim;
-    const int bkv = attn_detail::BKV;
+    const int impl = attn_impl();
+    const int bkv = impl == 2 ? attn2::BKV : attn_detail::BKV;
 
     const int v_hd = d.v_head_dim > 0 ? d.v_head_dim : hd;
     const int out_hd = d.out_head_dim > 0 ? d.out_head_dim : hd;
@@ -87,8 +114,28 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     // algorithmic FLOPs: 4*heads*hd*S^2 per sequence (bidirectional); causal work is supplied by the caller (flops_hint)
     double work = d.flops_hint;
     if (!varlen) work = 4.0 * d.heads * hd * (double)d.seq_len * d.seq_len * d.nseq;
-    // persistent grid: 2 CTAs per SM (registers / smem / TMEM allow exactly two), static round-robin over the items
     const int n_qblocks = varlen ? 0 : (d.seq_len + 127) / 128;
+    if (impl == 2) {
+        // persistent grid: one CTA per SM, each item = two query tiles sharing their K/V stream
+        a.pair_heads = (varlen && a.kv_group % 2 == 0) ? 1 : 0;
+        const long long n2 = varlen ? (long long)d.n_work * (a.pair_heads ? d.heads / 2 : d.heads)
+                                    : (long long)d.nseq * d.heads * ((n_qblocks + 1) / 2);
+        MJV_CHECK(n2 > 0 && n2 < (1LL << 31), MJV_ERR_ARG, "attention: bad item count %lld", n2);
+        a.n_items = (int)n2;
+        a.n_qblocks = n_qblocks;
+        dim3 grid2((unsigned)(n2 < sm_count() ? n2 : sm_count()), 1, 1);
+        if (hd == 64) {
+            if (d.causal) return launch_attn2_t<64, true>(tq, tk, tv, a, grid2, stream, work);
+            return launch_attn2_t<64, false>(tq, tk, tv, a, grid2, stream, work);
+        }
+        if (d.causal) return launch_attn2_t<128, true>(tq, tk, tv, a, grid2, stream, work);
+        return launch_attn2_t<128, false>(tq, tk, tv, a, grid2, stream, work);
+    }
+    // first generation: 2 CTAs per SM (registers / smem / TMEM allow exactly two), static round-robin over the items
+    if (varlen) {
+        // its work entries are plain (seq, q_block) pairs: the packed second block of attention2's MHA lists is not understood
+        MJV_CHECK(d.heads % d.kv_heads == 0, MJV_ERR_ARG, "attention: bad head counts");
+    }
     const long long n_items = varlen ? (long long)d.n_work * d.heads : (long long)d.nseq * d.heads * n_qblocks;
     MJV_CHECK(n_items > 0 && n_items < (1LL << 31), MJV_ERR_ARG, "attention: bad item count %lld", n_items);
     a.n_items = (int)n_items;

@@ -22,6 +22,30 @@ from . import _lib
 TOKEN_PATTERN = [92542, 92543, 525, 11353, 364]  # '<|im_end|><|im_start|>assistant\n' (moe_reward.py:48)
 
 
+def pack_work_entries(blocks, pair_blocks: bool) -> np.ndarray:
+    """int32 [n, 2] attention work list from (sequence, query_block) tuples, heaviest entry first (a causal block q reads
+    q+1 KV blocks). `pair_blocks`: two blocks of one sequence share an entry - low 16 bits of the second field hold the
+    larger block, the high 16 bits the other block + 1 (0 = none) - so one CTA streams their common K/V once
+    (csrc/attn2_sm100.cuh). Without it the second field is the plain block index."""
+    if not pair_blocks:
+        out = sorted(blocks, key=lambda t: -t[1])
+    else:
+        per_seq: dict[int, list[int]] = {}
+        for s, q in blocks:
+            per_seq.setdefault(s, []).append(q)
+        out = []
+        for s, qs in per_seq.items():
+            qs = sorted(set(qs), reverse=True)
+            if qs and qs[0] >= 0xFFFF:
+                raise ValueError("sequence too long for a packed attention work entry")
+            for i in range(0, len(qs), 2):
+                hi = qs[i]
+                lo = qs[i + 1] + 1 if i + 1 < len(qs) else 0
+                out.append((s, hi | (lo << 16)))
+        out.sort(key=lambda t: -(t[1] & 0xFFFF))
+    return np.asarray(out, dtype=np.int32).reshape(-1, 2)
+
+
 def find_token_for_gating(lst, token_pattern=None) -> int:
     """Index of the last occurrence of `token_pattern` in `lst` (moe_reward.py:50-57)."""
     pat = TOKEN_PATTERN if token_pattern is None else list(token_pattern)
@@ -263,14 +287,14 @@ class Engine:
         if img_rows.size < n_rows_vit:
             warnings.warn(f"warning: {n_rows_vit} visual embeddings for {img_rows.size} <IMG_CONTEXT> tokens; "
                           "truncating like the reference (modeling_internvl_chat.py:178-186)")
-        work = [(s, q) for s in range(B) for q in range((int(lengths[s]) + 127) // 128)]
-        work.sort(key=lambda t: -t[1])
-        work = np.asarray(work, dtype=np.int32).reshape(-1, 2)
+        # attention work entries (sequence, query block), heaviest first. With an even GQA group the kernel pairs the two
+        # query heads of a kv head itself; otherwise (MHA) two query blocks of one sequence travel in one entry
+        pair_blocks = (self.dims.llm_heads // self.dims.llm_kv_heads) % 2 != 0
+        work = pack_work_entries([(s, q) for s in range(B) for q in range((int(lengths[s]) + 127) // 128)], pair_blocks)
         gather = np.concatenate([cu[:-1] + last, cu[:-1] + gate]).astype(np.int32)
         # the last decoder layer only needs the attention blocks that contain a gathered row
-        work_last = sorted({(s, int(last[s]) // 128) for s in range(B)} | {(s, int(gate[s]) // 128) for s in range(B)},
-                           key=lambda t: -t[1])
-        work_last = np.asarray(work_last, dtype=np.int32).reshape(-1, 2)
+        work_last = pack_work_entries(
+            sorted({(s, int(last[s]) // 128) for s in range(B)} | {(s, int(gate[s]) // 128) for s in range(B)}), pair_blocks)
         meta = dict(token_ids=token_ids, row_pos=row_pos, row_vt=row_vt, img_rows=img_rows,
                     cu_seqlens=cu.astype(np.int32), vt_starts=vt_starts.astype(np.int32), work=work.reshape(-1),
                     gather_rows=gather, work_last=work_last.reshape(-1))

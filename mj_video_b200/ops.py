@@ -87,11 +87,12 @@ def attention(q, k, vt, out, *, head_dim, heads, kv_heads, causal, scale, q_col0
     return out
 
 
-def causal_work_list(lengths, block_q: int = 128):
-    """(sequence, q_block) pairs, heaviest (largest q_block) first so long causal rows start early."""
+def causal_work_list(lengths, block_q: int = 128, pair_blocks: bool = False):
+    """(sequence, q_block) entries, heaviest (largest q_block) first so long causal rows start early. `pair_blocks`
+    packs two blocks of a sequence into one entry (MHA shapes; see engine.pack_work_entries)."""
+    from .engine import pack_work_entries
     items = [(s, b) for s, n in enumerate(lengths) for b in range((n + block_q - 1) // block_q)]
-    items.sort(key=lambda t: -t[1])
-    return torch.tensor(items, dtype=torch.int32)
+    return torch.from_numpy(pack_work_entries(items, pair_blocks))
 
 
 def vt_layout(lengths, align: int = 8):

@@ -6,7 +6,7 @@
 // Why a second kernel (profiles/r01_ncu_full_attn_vit_v4.csv, source page): in attn_sm100.cuh a softmax warp spent only
 // 38 % of its time in the exponential loop; the rest was per-64-column-step overhead (barrier waits, spill reloads under
 // the 128-register cap of two CTAs per SM, instruction-cache misses of the doubly unrolled masked path, the item epilogue).
-// Here every step covers 128 columns, the two softmax warpgroups own 192 registers per thread (setmaxnreg), the masked
+// Here every step covers 128 columns, the two softmax warpgroups own 184 registers per thread (setmaxnreg), the masked
 // path is a small pre-pass in front of the one exponential loop, and the O / l -> bf16 epilogue runs on its own
 // warpgroup while the softmax warps already work on the next item.
 //
@@ -35,11 +35,15 @@ namespace attn2 {
 constexpr int BQ = 128;
 constexpr int BKV = 128;
 constexpr int kThreads = 512;
-constexpr int kNSB = 2;
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain: p stays below 2^8
+
+constexpr int kTraceEvents = 2048;  // per role (tools/attn_trace.py)
 
 template <int HD>
 struct Smem {
+    // score buffers in TMEM: head_dim 64 leaves room for three (3 x 128 + 2 x 64 = 512 columns), so S of a tile's NEXT block
+    // is computed while its softmax still works on the current one; head_dim 128 fills TMEM with two (2 x 128 + 2 x 128)
+    static constexpr int kNSB = HD == 64 ? 3 : 2;
     static constexpr int kQSets = HD == 64 ? 2 : 1;    // item-level double buffering of the Q tile pair
     static constexpr int kQBufs = 2 * kQSets;
     static constexpr int kKStages = HD == 64 ? 3 : 2;
@@ -169,6 +173,16 @@ __device__ __forceinline__ void exp_chunk(const uint32_t* v, uint32_t* pk, uint6
     }
 }
 
+// tools only: event k of a role -> trace[role*2*kTraceEvents + 2k] = clock64, [.. + 1] = tag << 32 | step
+__device__ __forceinline__ void trace_ev(long long* trace, int role, int& n, int tag, int step) {
+    if (n < kTraceEvents) {
+        long long* p = trace + (static_cast<long long>(role) * kTraceEvents + n) * 2;
+        p[0] = clock64();
+        p[1] = (static_cast<long long>(tag) << 32) | static_cast<unsigned>(step);
+        ++n;
+    }
+}
+
 }  // namespace attn2
 
 template <int HD, bool CAUSAL>
@@ -180,6 +194,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     constexpr int KS = L::kKStages;
     constexpr int VS = L::kVStages;
     constexpr int QSETS = L::kQSets;
+    constexpr int kNSB = L::kNSB;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem + L::kQOff;
     uint8_t* sK = smem + L::kKOff;
@@ -194,13 +209,14 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     uint64_t* v_empty = v_full + VS;         // [VS] V tile consumed by the P·V MMAs of both query tiles
     uint64_t* s_full = v_empty + VS;         // [kNSB] scores ready (MMA -> softmax)
     uint64_t* p_full = s_full + kNSB;        // [kNSB] probabilities written (softmax -> MMA), 4 warp arrivals
-    uint64_t* pv_done = p_full + kNSB;       // [2] every P·V of tile t (only waited on by the rare rescale)
-    uint64_t* o_done = pv_done + 2;          // [2] accumulator of tile t complete (MMA -> epilogue)
+    uint64_t* pv_done = p_full + kNSB;       // [kNSB] P·V of the step that used buffer b (only waited on by the rare rescale)
+    uint64_t* o_done = pv_done + kNSB;       // [2] accumulator of tile t complete (MMA -> epilogue)
     uint64_t* o_empty = o_done + 2;          // [2] accumulator read out (epilogue -> MMA / softmax), 4 warp arrivals
     uint64_t* l_ready = o_empty + 2;         // [2] row sums in smem (softmax -> epilogue), 4 warp arrivals
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_ready + 2);
 
-    const int warp = threadIdx.x >> 5;
+    // shuffled from lane 0 so that the compiler knows it is warp-uniform (role indices, TMEM addresses -> uniform registers)
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int n_items = args.n_items;
 
@@ -226,9 +242,9 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int b = 0; b < kNSB; ++b) {
             ptx::mbar_init(&s_full[b], 1);
             ptx::mbar_init(&p_full[b], 4);
+            ptx::mbar_init(&pv_done[b], 1);
         }
         for (int t = 0; t < 2; ++t) {
-            ptx::mbar_init(&pv_done[t], 1);
             ptx::mbar_init(&o_done[t], 1);
             ptx::mbar_init(&o_empty[t], 4);
             ptx::mbar_init(&l_ready[t], 4);
@@ -248,7 +264,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int wg = warp >> 2;
     if (wg < 2) {
         // ===================================================== softmax of query tile `wg` (TMEM lane == query row)
-        ptx::setmaxnreg_inc<192>();
+        ptx::setmaxnreg_inc<184>();
         const int tt = wg;
         const int qw = warp & 3;
         const int r = qw * 32 + lane;
@@ -256,9 +272,13 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t tmem_O = tmem_O0 + tt * HD + lane_sel;
         int sb = 0;           // score buffer of the next step (ring over ALL active steps of both tiles)
         uint32_t sph = 0;
-        uint32_t n_mine = 0;  // steps of this tile so far (global): pv_done[tt] has completed n_mine times when P·V caught up
+        uint32_t n_mine = 0;  // steps of this tile so far (tracing only)
+        int prev_sb = 0;      // ring position of this tile's previous step: its P·V signals pv_done[prev_sb] in phase prev_sph
+        uint32_t prev_sph = 0;
         uint32_t n_use = 0;   // items in which this tile was active so far
         const float scale_log2 = args.scale_log2;
+        const bool tracing = args.trace != nullptr && blockIdx.x == 0 && qw == 0 && lane == 0;
+        int n_tr = 0;
 
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const Item t = decode_item<CAUSAL>(args, it);
@@ -279,8 +299,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     if (++sb == kNSB) { sb = 0; sph ^= 1; }
                 }
                 if (j < my_nblk) {
+                    if (tracing) trace_ev(args.trace, tt, n_tr, 0, (int)n_mine);
                     ptx::mbar_wait_nocall(&s_full[sb], sph);
                     ptx::tc_fence_after();
+                    if (tracing) trace_ev(args.trace, tt, n_tr, 1, (int)n_mine);
                     const uint32_t tmem_S = tmem_base + sb * BKV + lane_sel;
                     const int kv0 = j * BKV;
                     const int valid = min(BKV, kv_end - kv0);                    // columns of this block that exist
@@ -320,8 +342,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                             need = true;
                         }
                         if (__any_sync(0xffffffffu, need)) {
-                            // the previous P·V of this tile must have landed in O_t: completion number n_mine of pv_done[tt]
-                            ptx::mbar_wait_nocall(&pv_done[tt], (n_mine - 1) & 1);
+                            // The previous P·V of this tile must have landed in O_t. pv_done is kept per score buffer so that
+                            // the parity wait is exact: that buffer's previous use completed before S of the previous step
+                            // was issued, and its next use needs a P that does not exist yet - the count is n-1 or n.
+                            ptx::mbar_wait_nocall(&pv_done[prev_sb], prev_sph);
                             ptx::tc_fence_after();
                             l_run *= alpha;
 #pragma unroll 1
@@ -336,6 +360,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                             ptx::tmem_wait_st();
                         }
                         // ---- p = exp2(s*c - m), row sum, bf16 pack; P (bf16 pairs) overwrites the first 64 columns of S
+                        if (tracing) trace_ev(args.trace, tt, n_tr, 2, (int)n_mine);
                         const uint64_t sc2 = ptx::pack_f32x2(scale_log2, scale_log2);
                         const uint64_t nm2 = ptx::pack_f32x2(-m_run, -m_run);
                         uint64_t ps2[4];
@@ -369,7 +394,9 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         ptx::unpack_f32x2(ptx::fadd2(ps2[0], ps2[1]), s0, s1);
                         ptx::unpack_f32x2(ptx::fadd2(ps2[2], ps2[3]), s2, s3);
                         l_run += (s0 + s1) + (s2 + s3);
+                        if (tracing) trace_ev(args.trace, tt, n_tr, 3, (int)n_mine);
                         ptx::tmem_wait_st();
+                        if (tracing) trace_ev(args.trace, tt, n_tr, 4, (int)n_mine);
                     }
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -377,6 +404,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     // slowest warp: its early arrivals land on the other buffer's barrier, never in a phase too early.
                     if (lane == 0) ptx::mbar_arrive(&p_full[sb]);
                     ++n_mine;
+                    prev_sb = sb;
+                    prev_sph = sph;
                     if (++sb == kNSB) { sb = 0; sph ^= 1; }
                 }
                 if (tt == 0 && j < other_nblk) {  // tile 1's step of this block follows in the ring
@@ -441,7 +470,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
         }
     } else {
-        ptx::setmaxnreg_dec<48>();
+        ptx::setmaxnreg_dec<64>();
         if (warp == 12) {
             // ===================================================== TMA producer
             if (ptx::elect_one()) {
@@ -484,109 +513,141 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
         } else if (warp == 13) {
             // ===================================================== MMA issuer
-            if (ptx::elect_one()) {
-                constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
-                constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD);
-                // ---- S stream: runs ahead of the P·V stream by up to kNSB steps, across item boundaries
-                int s_it = blockIdx.x;
-                bool s_done = s_it >= n_items;
-                ItemLite si;
-                si.nblk[0] = si.nblk[1] = si.kv_end[0] = si.kv_end[1] = si.nblk_max = 0;
-                if (!s_done) si = decode_lite<CAUSAL>(args, s_it);
-                int s_j = 0, s_t = 0;     // next S step (tile 0 is active in block 0 of every item)
-                int s_kst = 0;
-                uint32_t s_kph = 0;
-                uint32_t s_use[2] = {0, 0};
-                int gs = 0;               // S steps issued so far
-                auto issue_next_s = [&]() {
-                    const int t = s_t, j = s_j;
-                    const uint32_t use = sel2(t, s_use);
-                    const int buf = (use % QSETS) * 2 + t;
-                    if (j == 0) ptx::mbar_wait_nocall(&q_full[buf], (use / QSETS) & 1);
-                    const bool first_of_block = (t == 0) || !(j < si.nblk[0]);
-                    const bool last_of_block = (t == 1) || !(j < si.nblk[1]);
-                    if (first_of_block) ptx::mbar_wait_nocall(&k_full[s_kst], s_kph);
-                    ptx::tc_fence_after();
-                    const uint32_t q_addr = ptx::smem_u32(sQ + buf * L::kQBytes);
-                    const uint32_t k_addr = ptx::smem_u32(sK + s_kst * L::kKBytes);
-                    const uint32_t d = tmem_base + (gs % kNSB) * BKV;
+            // The whole warp runs the bookkeeping and the barrier waits (warp-uniform control flow keeps descriptors and
+            // addresses in uniform registers); only the elected lane issues tcgen05.mma / tcgen05.commit. The first version
+            // ran everything inside `if (elect_one())`: every MMA operand then went through R2UR and a rolled k-loop, the
+            // issue of one P·V took 650 cycles and the issuer, not the softmax, set the pace (tools/attn_trace.py).
+            const bool leader = ptx::elect_one();
+            constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
+            constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD);
+            const uint64_t q_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sQ));
+            const uint64_t k_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sK));
+            const uint64_t v_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sV));
+            // ---- S stream: runs ahead of the P·V stream by up to kNSB steps, across item boundaries
+            int s_it = blockIdx.x;
+            bool s_done = s_it >= n_items;
+            ItemLite si;
+            si.nblk[0] = si.nblk[1] = si.kv_end[0] = si.kv_end[1] = si.nblk_max = 0;
+            if (!s_done) si = decode_lite<CAUSAL>(args, s_it);
+            int s_j = 0, s_t = 0;     // next S step (tile 0 is active in block 0 of every item)
+            int s_kst = 0;
+            uint32_t s_kph = 0;
+            uint32_t s_use[2] = {0, 0};
+            int s_sb = 0;             // score buffer of the next S step
+            int gs = 0;               // S steps issued so far
+            auto issue_next_s = [&]() {
+                const int t = s_t, j = s_j;
+                const uint32_t use = sel2(t, s_use);
+                const int buf = (use % QSETS) * 2 + t;
+                if (j == 0) ptx::mbar_wait_nocall(&q_full[buf], (use / QSETS) & 1);
+                const bool first_of_block = (t == 0) || !(j < si.nblk[0]);
+                const bool last_of_block = (t == 1) || !(j < si.nblk[1]);
+                const bool last_of_tile = j == sel2(t, si.nblk) - 1;
+                if (first_of_block) ptx::mbar_wait_nocall(&k_full[s_kst], s_kph);
+                ptx::tc_fence_after();
+                const uint64_t a0 = q_desc0 + static_cast<uint64_t>((buf * L::kQBytes) >> 4);
+                const uint64_t b0 = k_desc0 + static_cast<uint64_t>((s_kst * L::kKBytes) >> 4);
+                const uint32_t d = tmem_base + s_sb * BKV;
+                if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < HD / 16; ++ks) {
-                        const uint64_t a = ptx::make_desc_sw128(q_addr + (ks >> 2) * (BQ * 128) + (ks & 3) * 32);
-                        const uint64_t b = ptx::make_desc_sw128(k_addr + (ks >> 2) * (BKV * 128) + (ks & 3) * 32);
+                        const uint64_t a = a0 + static_cast<uint64_t>(((ks >> 2) * (BQ * 128) + (ks & 3) * 32) >> 4);
+                        const uint64_t b = b0 + static_cast<uint64_t>(((ks >> 2) * (BKV * 128) + (ks & 3) * 32) >> 4);
                         ptx::mma_bf16_ss(d, a, b, idesc_s, ks != 0 ? 1u : 0u);
                     }
-                    ptx::mma_commit(&s_full[gs % kNSB]);
-                    if (last_of_block) {
-                        ptx::mma_commit(&k_empty[s_kst]);  // K tile free once the S MMAs of both tiles retire
-                        if (++s_kst == KS) { s_kst = 0; s_kph ^= 1; }
+                    ptx::mma_commit(&s_full[s_sb]);
+                    if (last_of_block) ptx::mma_commit(&k_empty[s_kst]);  // K tile free once the S MMAs of both tiles retire
+                    if (last_of_tile) ptx::mma_commit(&q_empty[buf]);     // last S of this tile in the item
+                }
+                __syncwarp();
+                if (last_of_block) {
+                    if (++s_kst == KS) { s_kst = 0; s_kph ^= 1; }
+                }
+                if (last_of_tile) {
+                    if (t != 0) ++s_use[1];
+                    else ++s_use[0];
+                }
+                ++gs;
+                if (++s_sb == kNSB) s_sb = 0;
+                // advance to the next active step
+                for (;;) {
+                    if (s_t == 0) {
+                        s_t = 1;
+                    } else {
+                        s_t = 0;
+                        ++s_j;
                     }
-                    if (j == sel2(t, si.nblk) - 1) {  // last S of this tile in the item: its Q tile can be replaced
-                        ptx::mma_commit(&q_empty[buf]);
-                        if (t != 0) ++s_use[1];
-                        else ++s_use[0];
-                    }
-                    ++gs;
-                    // advance to the next active step
-                    for (;;) {
-                        if (s_t == 0) {
-                            s_t = 1;
-                        } else {
-                            s_t = 0;
-                            ++s_j;
+                    if (s_j >= si.nblk_max) {
+                        s_it += gridDim.x;
+                        if (s_it >= n_items) {
+                            s_done = true;
+                            return;
                         }
-                        if (s_j >= si.nblk_max) {
-                            s_it += gridDim.x;
-                            if (s_it >= n_items) {
-                                s_done = true;
-                                return;
-                            }
-                            si = decode_lite<CAUSAL>(args, s_it);
-                            s_j = 0;
-                            s_t = 0;
-                        }
-                        if (s_j < sel2(s_t, si.nblk)) return;
+                        si = decode_lite<CAUSAL>(args, s_it);
+                        s_j = 0;
+                        s_t = 0;
                     }
-                };
-                // ---- P·V stream
-                int vst = 0;
-                uint32_t vph = 0;
-                int g = 0;
-                uint32_t o_use[2] = {0, 0};
-                for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-                    const ItemLite t = decode_lite<CAUSAL>(args, it);
-                    for (int j = 0; j < t.nblk_max; ++j) {
-                        const uint32_t v_addr = ptx::smem_u32(sV + vst * L::kVBytes);
+                    if (s_j < sel2(s_t, si.nblk)) return;
+                }
+            };
+            // ---- P·V stream
+            int vst = 0;
+            uint32_t vph = 0;
+            int g = 0;
+            int p_sb = 0;             // score buffer holding P of the next P·V step
+            uint32_t p_ph = 0;
+            uint32_t o_use[2] = {0, 0};
+            const bool tracing = args.trace != nullptr && blockIdx.x == 0 && leader;
+            int n_tr = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const ItemLite t = decode_lite<CAUSAL>(args, it);
+                for (int j = 0; j < t.nblk_max; ++j) {
+                    const uint64_t vb0 = v_desc0 + static_cast<uint64_t>((vst * L::kVBytes) >> 4);
+#pragma unroll 1
+                    for (int tt = 0; tt < 2; ++tt) {  // one copy of the code: the issuer's instruction footprint matters
+                        if (!(j < sel2(tt, t.nblk))) continue;
+                        while (gs < g + kNSB && !s_done) {
+                            issue_next_s();
+                            if (tracing) trace_ev(args.trace, 2, n_tr, 12, gs - 1);
+                        }
+                        const bool first_of_block = (tt == 0) || !(j < t.nblk[0]);
+                        const bool last_of_block = (tt == 1) || !(j < t.nblk[1]);
+                        const bool last_of_tile = j == sel2(tt, t.nblk) - 1;
+                        // waits that are normally satisfied long before P arrives come first: off the critical path
+                        if (first_of_block) ptx::mbar_wait_nocall(&v_full[vst], vph);
+                        const uint32_t ou = sel2(tt, o_use);
+                        // the epilogue has read out the previous item's accumulator of this tile
+                        if (j == 0 && ou > 0) ptx::mbar_wait_nocall(&o_empty[tt], (ou - 1) & 1);
+                        const int valid = min(BKV, sel2(tt, t.kv_end) - j * BKV);
+                        const int ksteps = (valid + 15) >> 4;
+                        const uint32_t p_tmem = tmem_base + p_sb * BKV;  // P_g: bf16 pairs in the first 64 columns
+                        const uint32_t o_tmem = tmem_O0 + tt * HD;
+                        ptx::mbar_wait_nocall(&p_full[p_sb], p_ph);
+                        ptx::tc_fence_after();
+                        if (tracing) trace_ev(args.trace, 2, n_tr, 10, g);
+                        if (leader) {
 #pragma unroll
-                        for (int tt = 0; tt < 2; ++tt) {
-                            if (!(j < t.nblk[tt])) continue;
-                            while (gs < g + kNSB && !s_done) issue_next_s();
-                            ptx::mbar_wait_nocall(&p_full[g % kNSB], (g / kNSB) & 1);
-                            const bool first_of_block = (tt == 0) || !(j < t.nblk[0]);
-                            const bool last_of_block = (tt == 1) || !(j < t.nblk[1]);
-                            if (first_of_block) ptx::mbar_wait_nocall(&v_full[vst], vph);
-                            // the epilogue has read out the previous item's accumulator of this tile
-                            if (j == 0 && o_use[tt] > 0) ptx::mbar_wait_nocall(&o_empty[tt], (o_use[tt] - 1) & 1);
-                            ptx::tc_fence_after();
-                            const int valid = min(BKV, t.kv_end[tt] - j * BKV);
-                            const int ksteps = (valid + 15) >> 4;
-                            const uint32_t p_tmem = tmem_base + (g % kNSB) * BKV;  // P_g: bf16 pairs in the first 64 columns
-                            const uint32_t o_tmem = tmem_O0 + tt * HD;
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                const uint64_t b = ptx::make_desc_sw128(v_addr + (ks >> 2) * (HD * 128) + (ks & 3) * 32);
-                                ptx::mma_bf16_ts(o_tmem, p_tmem + ks * 8, b, idesc_o, (j | ks) != 0 ? 1u : 0u);
+                            for (int ks = 0; ks < BKV / 16; ++ks) {
+                                if (ks < ksteps) {
+                                    const uint64_t b = vb0 + static_cast<uint64_t>(((ks >> 2) * (HD * 128) + (ks & 3) * 32) >> 4);
+                                    ptx::mma_bf16_ts(o_tmem, p_tmem + ks * 8, b, idesc_o, (j | ks) != 0 ? 1u : 0u);
+                                }
                             }
-                            ptx::mma_commit(&pv_done[tt]);
-                            if (j == t.nblk[tt] - 1) {
-                                ptx::mma_commit(&o_done[tt]);
-                                ++o_use[tt];
-                            }
-                            if (last_of_block) {
-                                ptx::mma_commit(&v_empty[vst]);
-                                if (++vst == VS) { vst = 0; vph ^= 1; }
-                            }
-                            ++g;
+                            ptx::mma_commit(&pv_done[p_sb]);
+                            if (last_of_tile) ptx::mma_commit(&o_done[tt]);
+                            if (last_of_block) ptx::mma_commit(&v_empty[vst]);
                         }
+                        __syncwarp();
+                        if (tracing) trace_ev(args.trace, 2, n_tr, 11, g);
+                        if (last_of_tile) {
+                            if (tt != 0) ++o_use[1];
+                            else ++o_use[0];
+                        }
+                        if (last_of_block) {
+                            if (++vst == VS) { vst = 0; vph ^= 1; }
+                        }
+                        ++g;
+                        if (++p_sb == kNSB) { p_sb = 0; p_ph ^= 1; }
                     }
                 }
             }

@@ -118,6 +118,8 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     if (impl == 2) {
         // persistent grid: one CTA per SM, each item = two query tiles sharing their K/V stream
         a.pair_heads = (varlen && a.kv_group % 2 == 0) ? 1 : 0;
+        if (const char* tp = getenv("MJV_ATTN_TRACE"))  // tools/attn_trace.py: device pointer (hex) of the event buffer
+            a.trace = reinterpret_cast<long long*>(strtoull(tp, nullptr, 16));
         const long long n2 = varlen ? (long long)d.n_work * (a.pair_heads ? d.heads / 2 : d.heads)
                                     : (long long)d.nseq * d.heads * ((n_qblocks + 1) / 2);
         MJV_CHECK(n2 > 0 && n2 < (1LL << 31), MJV_ERR_ARG, "attention: bad item count %lld", n2);

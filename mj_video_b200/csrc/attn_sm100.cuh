@@ -43,6 +43,7 @@ struct AttnArgs {
     int batched;            // 1: maps carry a per-sequence batch dim and rows are sequence-relative (ViT)
     int out_hd;             // columns per head written to `out` (<= HD, multiple of 16): narrow heads are stored packed
     int pair_heads;         // attention2 (attn2_sm100.cuh), varlen: the two query tiles of an item are the heads 2p, 2p+1
+    long long* trace;       // attention2, tools only: CTA 0 records (clock64, tag<<32|step) pairs per role here (or nullptr)
 };
 
 namespace attn_detail {

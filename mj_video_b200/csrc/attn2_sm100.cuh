@@ -15,7 +15,8 @@
 //   warps 4-7   softmax of query tile 1
 //   warps 8-11  epilogue: O_t / l -> bf16 -> global, then hands the accumulator back (o_empty)
 //   warp  12    TMA producer (Q tiles, K ring, V^T ring)
-//   warp  13    MMA issuer (S = Q·K^T into a ring of kNSB score buffers; O_t += P·V with P read from TMEM)
+//   warp  13    P·V issuer (O_t += P·V with P read from TMEM)
+//   warp  14    S issuer (S = Q·K^T into a ring of kNSB score buffers)
 // The two query tiles of an item share every K / V^T tile (one smem read stream for both):
 //   * bidirectional batched mode (ViT): consecutive 128-row blocks of one (sequence, head);
 //   * causal varlen mode with an even GQA group (InternLM2, 16 q / 8 kv heads): the two query heads of one kv head at the
@@ -23,8 +24,7 @@
 //   * causal varlen mode otherwise (MHA, e.g. the Llama / Phi-3 shaped branch): two query blocks of one head, packed by the
 //     host in one work entry (low 16 bits: first block, high 16 bits: second block + 1, or 0 for none).
 // Steps are numbered globally (g) in the order (block j, tile t) over the active tiles; step g uses score buffer
-// g % kNSB. tcgen05.mma executes in issue order, so S_{g+kNSB} (same buffer) is issued right after P_g·V and cannot
-// overwrite P_g early. The running maximum is updated lazily (only when it grows by more than 2^8), the rare rescale of
+// g % kNSB; S_{g+kNSB} (same buffer) is issued once pv_done signals that P_g·V has read P_g. The running maximum is updated lazily (only when it grows by more than 2^8), the rare rescale of
 // O_t happens in the softmax warps after waiting for the previous P·V of that tile (pv_done).
 #pragma once
 #include "attn_sm100.cuh"
@@ -157,19 +157,29 @@ __device__ __forceinline__ void max_chunk(const uint32_t* v, float* mx) {
         mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(v[C * 32 + i + 6]), __uint_as_float(v[C * 32 + i + 7])));
     }
 }
-// p = exp2(s*c - m) for the 32 scores of chunk C; packed bf16 pairs go to pk[16]; row-sum partials in ps2[4]
+// p = exp2(s*c - m) for the 32 scores of chunk C; packed bf16 pairs go to pk[16]; row-sum partials in ps2[4].
+// Software-pipelined by hand: the consumers (row sum, bf16 pack) of pair i are placed kExpDepth pairs behind its two
+// MUFU.EX2. ptxas otherwise consumes each pair right after the next pair's MUFUs are issued (16 cycles later), which is
+// shorter than the MUFU latency: a warp alone on its scheduler then stalls 8 cycles per pair (24 instead of 16 cycles).
+constexpr int kExpDepth = 3;
 template <int C>
 __device__ __forceinline__ void exp_chunk(const uint32_t* v, uint32_t* pk, uint64_t sc2, uint64_t nm2, uint64_t* ps2) {
+    float p[32];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const uint64_t t2 = ptx::ffma2(
-            ptx::pack_f32x2(__uint_as_float(v[C * 32 + 2 * i]), __uint_as_float(v[C * 32 + 2 * i + 1])), sc2, nm2);
-        float t0, t1;
-        ptx::unpack_f32x2(t2, t0, t1);
-        const float p0 = ptx::ex2_approx(t0);
-        const float p1 = ptx::ex2_approx(t1);
-        ps2[i & 3] = ptx::fadd2(ps2[i & 3], ptx::pack_f32x2(p0, p1));
-        pk[i] = ptx::pack_bf16x2(p0, p1);
+    for (int i = 0; i < 16 + kExpDepth; ++i) {
+        if (i < 16) {
+            const uint64_t t2 = ptx::ffma2(
+                ptx::pack_f32x2(__uint_as_float(v[C * 32 + 2 * i]), __uint_as_float(v[C * 32 + 2 * i + 1])), sc2, nm2);
+            float t0, t1;
+            ptx::unpack_f32x2(t2, t0, t1);
+            p[2 * i] = ptx::ex2_approx(t0);
+            p[2 * i + 1] = ptx::ex2_approx(t1);
+        }
+        if (i >= kExpDepth) {
+            const int k = i - kExpDepth;
+            ps2[k & 3] = ptx::fadd2(ps2[k & 3], ptx::pack_f32x2(p[2 * k], p[2 * k + 1]));
+            pk[k] = ptx::pack_bf16x2(p[2 * k], p[2 * k + 1]);
+        }
     }
 }
 
@@ -251,7 +261,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 14) {
+    if (warp == 15) {
         ptx::tmem_alloc(tmem_slot, 512);
         ptx::tmem_relinquish();
     }
@@ -483,7 +493,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     for (int tt = 0; tt < 2; ++tt) {
                         if (t.nblk[tt] == 0) continue;
                         const int buf = (n_use[tt] % QSETS) * 2 + tt;
-                        ptx::mbar_wait_nocall(&q_empty[buf], ((n_use[tt] / QSETS) & 1) ^ 1);
+                        ptx::mbar_wait_spin(&q_empty[buf], ((n_use[tt] / QSETS) & 1) ^ 1);
                         ptx::mbar_expect_tx(&q_full[buf], L::kQBytes);
 #pragma unroll
                         for (int kd = 0; kd < HD / 64; ++kd)
@@ -493,7 +503,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         ++n_use[tt];
                     }
                     for (int j = 0; j < t.nblk_max; ++j) {
-                        ptx::mbar_wait_nocall(&k_empty[kst], kph ^ 1);
+                        ptx::mbar_wait_spin(&k_empty[kst], kph ^ 1);
                         ptx::mbar_expect_tx(&k_full[kst], L::kKBytes);
 #pragma unroll
                         for (int kd = 0; kd < HD / 64; ++kd)
@@ -501,7 +511,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                              args.k_col0 + t.kvh * HD + kd * 64, t.tma_row0 + j * BKV, t.tma_batch,
                                              ptx::kEvictLast);
                         if (++kst == KS) { kst = 0; kph ^= 1; }
-                        ptx::mbar_wait_nocall(&v_empty[vst], vph ^ 1);
+                        ptx::mbar_wait_spin(&v_empty[vst], vph ^ 1);
                         ptx::mbar_expect_tx(&v_full[vst], L::kVBytes);
 #pragma unroll
                         for (int half = 0; half < 2; ++half)
@@ -512,85 +522,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 }
             }
         } else if (warp == 13) {
-            // ===================================================== MMA issuer
-            // The whole warp runs the bookkeeping and the barrier waits (warp-uniform control flow keeps descriptors and
-            // addresses in uniform registers); only the elected lane issues tcgen05.mma / tcgen05.commit. The first version
-            // ran everything inside `if (elect_one())`: every MMA operand then went through R2UR and a rolled k-loop, the
-            // issue of one P·V took 650 cycles and the issuer, not the softmax, set the pace (tools/attn_trace.py).
+            // ===================================================== P·V issuer
+            // Two issuing warps (this one and the S issuer below) instead of one: a single issuer is blocked while the tensor
+            // pipe drains its queue, so with one warp the 4 S MMAs of step g+kNSB sat between P_g·V and the wait for P_{g+1}
+            // (1100 cycles per step, tools/attn_trace.py) and the issuer, not the softmax, set the pace. Both warps run
+            // their bookkeeping and barrier waits warp-uniformly (descriptors stay in uniform registers); only the elected
+            // lane issues tcgen05.mma / tcgen05.commit. MMAs of different threads are not ordered against each other, so
+            // the reuse of a score buffer is explicit: the S issuer waits for pv_done[b] of the step that last read it.
             const bool leader = ptx::elect_one();
-            constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
             constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD);
-            const uint64_t q_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sQ));
-            const uint64_t k_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sK));
             const uint64_t v_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sV));
-            // ---- S stream: runs ahead of the P·V stream by up to kNSB steps, across item boundaries
-            int s_it = blockIdx.x;
-            bool s_done = s_it >= n_items;
-            ItemLite si;
-            si.nblk[0] = si.nblk[1] = si.kv_end[0] = si.kv_end[1] = si.nblk_max = 0;
-            if (!s_done) si = decode_lite<CAUSAL>(args, s_it);
-            int s_j = 0, s_t = 0;     // next S step (tile 0 is active in block 0 of every item)
-            int s_kst = 0;
-            uint32_t s_kph = 0;
-            uint32_t s_use[2] = {0, 0};
-            int s_sb = 0;             // score buffer of the next S step
-            int gs = 0;               // S steps issued so far
-            auto issue_next_s = [&]() {
-                const int t = s_t, j = s_j;
-                const uint32_t use = sel2(t, s_use);
-                const int buf = (use % QSETS) * 2 + t;
-                if (j == 0) ptx::mbar_wait_nocall(&q_full[buf], (use / QSETS) & 1);
-                const bool first_of_block = (t == 0) || !(j < si.nblk[0]);
-                const bool last_of_block = (t == 1) || !(j < si.nblk[1]);
-                const bool last_of_tile = j == sel2(t, si.nblk) - 1;
-                if (first_of_block) ptx::mbar_wait_nocall(&k_full[s_kst], s_kph);
-                ptx::tc_fence_after();
-                const uint64_t a0 = q_desc0 + static_cast<uint64_t>((buf * L::kQBytes) >> 4);
-                const uint64_t b0 = k_desc0 + static_cast<uint64_t>((s_kst * L::kKBytes) >> 4);
-                const uint32_t d = tmem_base + s_sb * BKV;
-                if (leader) {
-#pragma unroll
-                    for (int ks = 0; ks < HD / 16; ++ks) {
-                        const uint64_t a = a0 + static_cast<uint64_t>(((ks >> 2) * (BQ * 128) + (ks & 3) * 32) >> 4);
-                        const uint64_t b = b0 + static_cast<uint64_t>(((ks >> 2) * (BKV * 128) + (ks & 3) * 32) >> 4);
-                        ptx::mma_bf16_ss(d, a, b, idesc_s, ks != 0 ? 1u : 0u);
-                    }
-                    ptx::mma_commit(&s_full[s_sb]);
-                    if (last_of_block) ptx::mma_commit(&k_empty[s_kst]);  // K tile free once the S MMAs of both tiles retire
-                    if (last_of_tile) ptx::mma_commit(&q_empty[buf]);     // last S of this tile in the item
-                }
-                __syncwarp();
-                if (last_of_block) {
-                    if (++s_kst == KS) { s_kst = 0; s_kph ^= 1; }
-                }
-                if (last_of_tile) {
-                    if (t != 0) ++s_use[1];
-                    else ++s_use[0];
-                }
-                ++gs;
-                if (++s_sb == kNSB) s_sb = 0;
-                // advance to the next active step
-                for (;;) {
-                    if (s_t == 0) {
-                        s_t = 1;
-                    } else {
-                        s_t = 0;
-                        ++s_j;
-                    }
-                    if (s_j >= si.nblk_max) {
-                        s_it += gridDim.x;
-                        if (s_it >= n_items) {
-                            s_done = true;
-                            return;
-                        }
-                        si = decode_lite<CAUSAL>(args, s_it);
-                        s_j = 0;
-                        s_t = 0;
-                    }
-                    if (s_j < sel2(s_t, si.nblk)) return;
-                }
-            };
-            // ---- P·V stream
             int vst = 0;
             uint32_t vph = 0;
             int g = 0;
@@ -606,23 +547,19 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll 1
                     for (int tt = 0; tt < 2; ++tt) {  // one copy of the code: the issuer's instruction footprint matters
                         if (!(j < sel2(tt, t.nblk))) continue;
-                        while (gs < g + kNSB && !s_done) {
-                            issue_next_s();
-                            if (tracing) trace_ev(args.trace, 2, n_tr, 12, gs - 1);
-                        }
                         const bool first_of_block = (tt == 0) || !(j < t.nblk[0]);
                         const bool last_of_block = (tt == 1) || !(j < t.nblk[1]);
                         const bool last_of_tile = j == sel2(tt, t.nblk) - 1;
                         // waits that are normally satisfied long before P arrives come first: off the critical path
-                        if (first_of_block) ptx::mbar_wait_nocall(&v_full[vst], vph);
+                        if (first_of_block) ptx::mbar_wait_spin(&v_full[vst], vph);
                         const uint32_t ou = sel2(tt, o_use);
                         // the epilogue has read out the previous item's accumulator of this tile
-                        if (j == 0 && ou > 0) ptx::mbar_wait_nocall(&o_empty[tt], (ou - 1) & 1);
+                        if (j == 0 && ou > 0) ptx::mbar_wait_spin(&o_empty[tt], (ou - 1) & 1);
                         const int valid = min(BKV, sel2(tt, t.kv_end) - j * BKV);
                         const int ksteps = (valid + 15) >> 4;
                         const uint32_t p_tmem = tmem_base + p_sb * BKV;  // P_g: bf16 pairs in the first 64 columns
                         const uint32_t o_tmem = tmem_O0 + tt * HD;
-                        ptx::mbar_wait_nocall(&p_full[p_sb], p_ph);
+                        ptx::mbar_wait_spin(&p_full[p_sb], p_ph);
                         ptx::tc_fence_after();
                         if (tracing) trace_ev(args.trace, 2, n_tr, 10, g);
                         if (leader) {
@@ -651,12 +588,71 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     }
                 }
             }
+        } else if (warp == 14) {
+            // ===================================================== S issuer: S_g = Q_t · K_j^T into score buffer g % kNSB
+            const bool leader = ptx::elect_one();
+            constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
+            const uint64_t q_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sQ));
+            const uint64_t k_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sK));
+            int kst = 0;
+            uint32_t kph = 0;
+            uint32_t q_use[2] = {0, 0};
+            int sb = 0;               // score buffer of the next S step
+            uint32_t sph = 0;         // parity of its CURRENT use; its previous use completed pv_done[sb] in phase sph ^ 1
+            bool wrapped = false;     // every buffer has been used once
+            const bool tracing = args.trace != nullptr && blockIdx.x == 0 && leader;
+            int n_tr = 0;
+            int gs = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const ItemLite t = decode_lite<CAUSAL>(args, it);
+                for (int j = 0; j < t.nblk_max; ++j) {
+                    const uint64_t b0 = k_desc0 + static_cast<uint64_t>((kst * L::kKBytes) >> 4);
+#pragma unroll 1
+                    for (int tt = 0; tt < 2; ++tt) {
+                        if (!(j < sel2(tt, t.nblk))) continue;
+                        const bool first_of_block = (tt == 0) || !(j < t.nblk[0]);
+                        const bool last_of_block = (tt == 1) || !(j < t.nblk[1]);
+                        const bool last_of_tile = j == sel2(tt, t.nblk) - 1;
+                        const uint32_t use = sel2(tt, q_use);
+                        const int buf = (use % QSETS) * 2 + tt;
+                        if (j == 0) ptx::mbar_wait_spin(&q_full[buf], (use / QSETS) & 1);
+                        if (first_of_block) ptx::mbar_wait_spin(&k_full[kst], kph);
+                        // the P·V that read this buffer's previous contents (P of step gs - kNSB) has completed
+                        if (wrapped) ptx::mbar_wait_spin(&pv_done[sb], sph ^ 1);
+                        ptx::tc_fence_after();
+                        const uint64_t a0 = q_desc0 + static_cast<uint64_t>((buf * L::kQBytes) >> 4);
+                        const uint32_t d = tmem_base + sb * BKV;
+                        if (leader) {
+#pragma unroll
+                            for (int ks = 0; ks < HD / 16; ++ks) {
+                                const uint64_t a = a0 + static_cast<uint64_t>(((ks >> 2) * (BQ * 128) + (ks & 3) * 32) >> 4);
+                                const uint64_t b = b0 + static_cast<uint64_t>(((ks >> 2) * (BKV * 128) + (ks & 3) * 32) >> 4);
+                                ptx::mma_bf16_ss(d, a, b, idesc_s, ks != 0 ? 1u : 0u);
+                            }
+                            ptx::mma_commit(&s_full[sb]);
+                            if (last_of_block) ptx::mma_commit(&k_empty[kst]);  // K tile free once the S MMAs of both tiles retire
+                            if (last_of_tile) ptx::mma_commit(&q_empty[buf]);   // last S of this tile in the item
+                        }
+                        __syncwarp();
+                        if (tracing) trace_ev(args.trace, 3, n_tr, 12, gs);
+                        if (last_of_block) {
+                            if (++kst == KS) { kst = 0; kph ^= 1; }
+                        }
+                        if (last_of_tile) {
+                            if (tt != 0) ++q_use[1];
+                            else ++q_use[0];
+                        }
+                        ++gs;
+                        if (++sb == kNSB) { sb = 0; sph ^= 1; wrapped = true; }
+                    }
+                }
+            }
         }
     }
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 14) {
+    if (warp == 15) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, 512);
     }

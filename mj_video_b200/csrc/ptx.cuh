@@ -98,6 +98,14 @@ __device__ __forceinline__ void mbar_wait_nocall(uint64_t* bar, uint32_t parity)
     }
 }
 
+// Bare spin (three instructions). For roles whose stall is always also seen by a watchdog-carrying waiter of the same
+// CTA (attention2: every hand-off cycle passes through the softmax warps' s_full wait), and whose instruction footprint
+// matters more than a second watchdog.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

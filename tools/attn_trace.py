@@ -3,7 +3,7 @@
 CTA 0 records (clock64, tag, step) events for three roles into a device buffer handed over through MJV_ATTN_TRACE:
   role 0/1  softmax warp 0 of query tile 0/1: 0 before the s_full wait, 1 after it, 2 max known (before the exponentials),
             3 exponentials + P stores issued, 4 P stores complete (just before the p_full arrive)
-  role 2    MMA issuer: 12 after issuing an S step, 10 after the p_full wait of a step, 11 after issuing its P·V
+  role 2    P·V issuer: 10 after the p_full wait of a step, 11 after issuing its P·V;  role 3  S issuer: 12 after issuing S of a step
 Prints median cycle counts per phase. Usage: python tools/attn_trace.py [vit|llm]
 """
 from __future__ import annotations
@@ -48,7 +48,7 @@ def run_llm(lens=None, H=16, Hkv=8, hd=128):
 
 
 def summarize(buf, name):
-    ev = buf.view(3, EV, 2).cpu().numpy()
+    ev = buf.view(4, EV, 2).cpu().numpy()
     res = {}
     for role in (0, 1):
         e = ev[role]
@@ -71,15 +71,16 @@ def summarize(buf, name):
     clk, tag, step = e[:n, 0], e[:n, 1] >> 32, e[:n, 1] & 0xFFFFFFFF
     t10 = {int(s): int(c) for c, t, s in zip(clk, tag, step) if t == 10}
     t11 = {int(s): int(c) for c, t, s in zip(clk, tag, step) if t == 11}
-    t12 = {int(s): int(c) for c, t, s in zip(clk, tag, step) if t == 12}
     ks = sorted(t10)[16:]
-    t12v = np.array(sorted(t12.values()))
-    def next_s(c):
-        i = np.searchsorted(t12v, c)
-        return int(t12v[i] - c) if i < len(t12v) else -1
-    res["mma"] = {"events": n, "period_per_step": float(np.median(np.diff([t10[s] for s in ks]))),
-                  "pv_issue": float(np.median([t11[s] - t10[s] for s in ks if s in t11])),
-                  "s_issue_after_pv": float(np.median([next_s(t11[s]) for s in ks if s in t11]))}
+    res["pv_issuer"] = {"events": n, "period_per_step": float(np.median(np.diff([t10[s] for s in ks]))),
+                        "pv_issue": float(np.median([t11[s] - t10[s] for s in ks if s in t11])),
+                        "wait_for_p": float(np.median([t10[s + 1] - t11[s] for s in ks if s + 1 in t10 and s in t11]))}
+    e = ev[3]
+    n = int((e[:, 0] != 0).sum())
+    clk, step = e[:n, 0], e[:n, 1] & 0xFFFFFFFF
+    t12 = {int(s): int(c) for c, s in zip(clk, step)}
+    res["s_issuer"] = {"events": n, "period_per_step": float(np.median(np.diff([t12[s] for s in sorted(t12)[16:]]))),
+                       "s_issued_before_p_seen": float(np.median([t10[s] - t12[s] for s in ks if s in t12]))}
     # hand-off: p_full arrive (tag 4 of softmax) -> MMA saw it (tag 10)
     print(name, json.dumps(res, indent=1))
     return res
@@ -92,13 +93,13 @@ if __name__ == "__main__":
         fn = run_vit() if w == "vit" else run_llm()
         fn()
         torch.cuda.synchronize()
-        buf = torch.zeros(3 * EV * 2, dtype=torch.int64, device=dev)
+        buf = torch.zeros(4 * EV * 2, dtype=torch.int64, device=dev)
         os.environ["MJV_ATTN_TRACE"] = hex(buf.data_ptr())
         fn()
         torch.cuda.synchronize()
         os.environ.pop("MJV_ATTN_TRACE")
         out[w] = summarize(buf, w)
-        raw = buf.view(3, EV, 2).cpu().numpy()
+        raw = buf.view(4, EV, 2).cpu().numpy()
         np.save(f"gpurun_out/attn_trace_{w}.npy", raw)
     with open("gpurun_out/attn_trace.json", "w") as f:
         json.dump(out, f, indent=1)

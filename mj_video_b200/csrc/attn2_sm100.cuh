@@ -195,7 +195,9 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int& n, int
 
 }  // namespace attn2
 
-template <int HD, bool CAUSAL>
+// DBG (tools only, selected by the launcher when MJV_ATTN_TRACE is set): every barrier wait carries a watchdog that records
+// which wait wedged (role/barrier code) into the host-pinned trace buffer before trapping.
+template <int HD, bool CAUSAL, bool DBG = false>
 __global__ void __launch_bounds__(attn2::kThreads, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnArgs args) {
@@ -217,8 +219,13 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     uint64_t* k_empty = k_full + KS;         // [KS] K tile consumed by the S MMAs of both query tiles
     uint64_t* v_full = k_empty + KS;         // [VS]
     uint64_t* v_empty = v_full + VS;         // [VS] V tile consumed by the P·V MMAs of both query tiles
-    uint64_t* s_full = v_empty + VS;         // [kNSB] scores ready (MMA -> softmax)
-    uint64_t* p_full = s_full + kNSB;        // [kNSB] probabilities written (softmax -> MMA), 4 warp arrivals
+    // s_full is kept PER QUERY TILE (slot = that tile's step count % kNSB), not per score buffer: an mbarrier wait only knows
+    // a phase parity, so a waiter must see every completion of the barrier it waits on. With per-buffer barriers the
+    // warpgroup of a tile that sits out an item (single-tile item) had to watch foreign steps without gating them, and a
+    // slow warp was lapped by two phases near the end of a launch (wedged pipeline). Per tile, every completion is one of
+    // the waiter's own steps, and slot reuse (kNSB tile steps later) is gated by its own P of the earlier step.
+    uint64_t* s_full = v_empty + VS;         // [2][kNSB] scores ready (S issuer -> softmax of that tile)
+    uint64_t* p_full = s_full + 2 * kNSB;    // [kNSB] probabilities written (softmax -> P·V issuer), 4 warp arrivals
     uint64_t* pv_done = p_full + kNSB;       // [kNSB] P·V of the step that used buffer b (only waited on by the rare rescale)
     uint64_t* o_done = pv_done + kNSB;       // [2] accumulator of tile t complete (MMA -> epilogue)
     uint64_t* o_empty = o_done + 2;          // [2] accumulator read out (epilogue -> MMA / softmax), 4 warp arrivals
@@ -229,6 +236,17 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int n_items = args.n_items;
+    // wait_wd: waits that always carry the watchdog; wait_sp: bare spins (watchdog + record only in the DBG build)
+    long long* const dbg_rec = DBG ? args.trace + 4 * 2 * kTraceEvents + 8 * (threadIdx.x >> 5) : nullptr;
+    long long dbg_aux = 0;  // DBG: item << 32 | step counter of the role, reported when a wait wedges
+    auto wait_wd = [&](uint64_t* bar, uint32_t parity, int code) {
+        if constexpr (DBG) ptx::mbar_wait_dbg(bar, parity, dbg_rec, code, dbg_aux);
+        else ptx::mbar_wait_nocall(bar, parity);
+    };
+    auto wait_sp = [&](uint64_t* bar, uint32_t parity, int code) {
+        if constexpr (DBG) ptx::mbar_wait_dbg(bar, parity, dbg_rec, code, dbg_aux);
+        else ptx::mbar_wait_spin(bar, parity);
+    };
 
     if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need a 1024-byte aligned base
     if (warp == 12 && lane == 0) {
@@ -251,6 +269,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         for (int b = 0; b < kNSB; ++b) {
             ptx::mbar_init(&s_full[b], 1);
+            ptx::mbar_init(&s_full[kNSB + b], 1);
             ptx::mbar_init(&p_full[b], 4);
             ptx::mbar_init(&pv_done[b], 1);
         }
@@ -281,7 +300,9 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t lane_sel = static_cast<uint32_t>(qw * 32) << 16;
         const uint32_t tmem_O = tmem_O0 + tt * HD + lane_sel;
         int sb = 0;           // score buffer of the next step (ring over ALL active steps of both tiles)
-        uint32_t sph = 0;
+        uint32_t sph = 0;     // ... and the parity of that ring pass (p_full / pv_done phases)
+        int my_slot = 0;      // s_full slot of this tile's next step (ring over its OWN steps)
+        uint32_t my_ph = 0;
         uint32_t n_mine = 0;  // steps of this tile so far (tracing only)
         int prev_sb = 0;      // ring position of this tile's previous step: its P·V signals pv_done[prev_sb] in phase prev_sph
         uint32_t prev_sph = 0;
@@ -301,17 +322,15 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             float l_run = 0.0f;
 
             for (int j = 0; j < t.nblk_max; ++j) {
+                if constexpr (DBG) dbg_aux = (static_cast<long long>(it) << 32) | (static_cast<long long>(j) << 16) | (sb << 8) | sph;
                 if (tt == 1 && j < other_nblk) {  // tile 0's step of this block comes first in the ring
-                    // mbarrier waits only know a phase parity: a warpgroup that owns no step in this block must still
-                    // OBSERVE the foreign step's completion, or it runs ahead (e.g. through a whole single-tile item) and
-                    // its next own wait is satisfied by a completion two phases too early
-                    if (!(j < my_nblk)) ptx::mbar_wait_nocall(&s_full[sb], sph);
                     if (++sb == kNSB) { sb = 0; sph ^= 1; }
                 }
                 if (j < my_nblk) {
                     if (tracing) trace_ev(args.trace, tt, n_tr, 0, (int)n_mine);
-                    ptx::mbar_wait_nocall(&s_full[sb], sph);
+                    wait_wd(&s_full[tt * kNSB + my_slot], my_ph, 1);
                     ptx::tc_fence_after();
+                    if (++my_slot == kNSB) { my_slot = 0; my_ph ^= 1; }
                     if (tracing) trace_ev(args.trace, tt, n_tr, 1, (int)n_mine);
                     const uint32_t tmem_S = tmem_base + sb * BKV + lane_sel;
                     const int kv0 = j * BKV;
@@ -355,7 +374,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                             // The previous P·V of this tile must have landed in O_t. pv_done is kept per score buffer so that
                             // the parity wait is exact: that buffer's previous use completed before S of the previous step
                             // was issued, and its next use needs a P that does not exist yet - the count is n-1 or n.
-                            ptx::mbar_wait_nocall(&pv_done[prev_sb], prev_sph);
+                            wait_wd(&pv_done[prev_sb], prev_sph, 2);
                             ptx::tc_fence_after();
                             l_run *= alpha;
 #pragma unroll 1
@@ -410,8 +429,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     }
                     ptx::tc_fence_before();
                     __syncwarp();
-                    // A warp without rows still waits for s_full above, so it can run at most kNSB-1 steps ahead of the
-                    // slowest warp: its early arrivals land on the other buffer's barrier, never in a phase too early.
+                    // A warp without rows still waits for s_full above: S of the step that reuses this buffer (and this p_full
+                    // barrier) is only issued after the P·V of this step, i.e. after all four arrivals of this phase.
                     if (lane == 0) ptx::mbar_arrive(&p_full[sb]);
                     ++n_mine;
                     prev_sb = sb;
@@ -419,13 +438,12 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     if (++sb == kNSB) { sb = 0; sph ^= 1; }
                 }
                 if (tt == 0 && j < other_nblk) {  // tile 1's step of this block follows in the ring
-                    if (!(j < my_nblk)) ptx::mbar_wait_nocall(&s_full[sb], sph);
                     if (++sb == kNSB) { sb = 0; sph ^= 1; }
                 }
             }
             if (my_nblk > 0) {
                 // hand the row sums to the epilogue warpgroup (which must be done with the previous item's)
-                if (n_use > 0) ptx::mbar_wait_nocall(&o_empty[tt], (n_use - 1) & 1);
+                if (n_use > 0) wait_wd(&o_empty[tt], (n_use - 1) & 1, 3);
                 sL[tt * BQ + r] = l_run;
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&l_ready[tt]);
@@ -444,8 +462,9 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
                 if (t.nblk[tt] == 0) continue;
-                ptx::mbar_wait_nocall(&l_ready[tt], n_use[tt] & 1);
-                ptx::mbar_wait_nocall(&o_done[tt], n_use[tt] & 1);
+                if constexpr (DBG) dbg_aux = (static_cast<long long>(it) << 32) | (tt << 16) | n_use[tt];
+                wait_wd(&l_ready[tt], n_use[tt] & 1, 4);
+                wait_wd(&o_done[tt], n_use[tt] & 1, 5);
                 ptx::tc_fence_after();
                 const int qrow = t.q0[tt] + r;
                 const bool warp_has_rows = (t.q0[tt] + qw * 32) < t.len;
@@ -493,7 +512,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     for (int tt = 0; tt < 2; ++tt) {
                         if (t.nblk[tt] == 0) continue;
                         const int buf = (n_use[tt] % QSETS) * 2 + tt;
-                        ptx::mbar_wait_spin(&q_empty[buf], ((n_use[tt] / QSETS) & 1) ^ 1);
+                        wait_sp(&q_empty[buf], ((n_use[tt] / QSETS) & 1) ^ 1, 10);
                         ptx::mbar_expect_tx(&q_full[buf], L::kQBytes);
 #pragma unroll
                         for (int kd = 0; kd < HD / 64; ++kd)
@@ -503,7 +522,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         ++n_use[tt];
                     }
                     for (int j = 0; j < t.nblk_max; ++j) {
-                        ptx::mbar_wait_spin(&k_empty[kst], kph ^ 1);
+                        if constexpr (DBG) dbg_aux = (static_cast<long long>(it) << 32) | (static_cast<long long>(j) << 16) | (vst << 8) | vph;
+                        wait_sp(&k_empty[kst], kph ^ 1, 11);
                         ptx::mbar_expect_tx(&k_full[kst], L::kKBytes);
 #pragma unroll
                         for (int kd = 0; kd < HD / 64; ++kd)
@@ -511,7 +531,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                              args.k_col0 + t.kvh * HD + kd * 64, t.tma_row0 + j * BKV, t.tma_batch,
                                              ptx::kEvictLast);
                         if (++kst == KS) { kst = 0; kph ^= 1; }
-                        ptx::mbar_wait_spin(&v_empty[vst], vph ^ 1);
+                        wait_sp(&v_empty[vst], vph ^ 1, 12);
                         ptx::mbar_expect_tx(&v_full[vst], L::kVBytes);
 #pragma unroll
                         for (int half = 0; half < 2; ++half)
@@ -547,19 +567,20 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll 1
                     for (int tt = 0; tt < 2; ++tt) {  // one copy of the code: the issuer's instruction footprint matters
                         if (!(j < sel2(tt, t.nblk))) continue;
+                        if constexpr (DBG) dbg_aux = (static_cast<long long>(it) << 32) | (static_cast<long long>(g) << 8) | (p_sb << 4) | p_ph;
                         const bool first_of_block = (tt == 0) || !(j < t.nblk[0]);
                         const bool last_of_block = (tt == 1) || !(j < t.nblk[1]);
                         const bool last_of_tile = j == sel2(tt, t.nblk) - 1;
                         // waits that are normally satisfied long before P arrives come first: off the critical path
-                        if (first_of_block) ptx::mbar_wait_spin(&v_full[vst], vph);
+                        if (first_of_block) wait_sp(&v_full[vst], vph, 20);
                         const uint32_t ou = sel2(tt, o_use);
                         // the epilogue has read out the previous item's accumulator of this tile
-                        if (j == 0 && ou > 0) ptx::mbar_wait_spin(&o_empty[tt], (ou - 1) & 1);
+                        if (j == 0 && ou > 0) wait_sp(&o_empty[tt], (ou - 1) & 1, 21);
                         const int valid = min(BKV, sel2(tt, t.kv_end) - j * BKV);
                         const int ksteps = (valid + 15) >> 4;
                         const uint32_t p_tmem = tmem_base + p_sb * BKV;  // P_g: bf16 pairs in the first 64 columns
                         const uint32_t o_tmem = tmem_O0 + tt * HD;
-                        ptx::mbar_wait_spin(&p_full[p_sb], p_ph);
+                        wait_sp(&p_full[p_sb], p_ph, 22);
                         ptx::tc_fence_after();
                         if (tracing) trace_ev(args.trace, 2, n_tr, 10, g);
                         if (leader) {
@@ -597,6 +618,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             int kst = 0;
             uint32_t kph = 0;
             uint32_t q_use[2] = {0, 0};
+            int t_slot[2] = {0, 0};   // s_full slot of each tile's next step
             int sb = 0;               // score buffer of the next S step
             uint32_t sph = 0;         // parity of its CURRENT use; its previous use completed pv_done[sb] in phase sph ^ 1
             bool wrapped = false;     // every buffer has been used once
@@ -615,10 +637,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         const bool last_of_tile = j == sel2(tt, t.nblk) - 1;
                         const uint32_t use = sel2(tt, q_use);
                         const int buf = (use % QSETS) * 2 + tt;
-                        if (j == 0) ptx::mbar_wait_spin(&q_full[buf], (use / QSETS) & 1);
-                        if (first_of_block) ptx::mbar_wait_spin(&k_full[kst], kph);
+                        if constexpr (DBG) dbg_aux = (static_cast<long long>(it) << 32) | (static_cast<long long>(gs) << 8) | (sb << 4) | sph;
+                        if (j == 0) wait_sp(&q_full[buf], (use / QSETS) & 1, 30);
+                        if (first_of_block) wait_sp(&k_full[kst], kph, 31);
                         // the P·V that read this buffer's previous contents (P of step gs - kNSB) has completed
-                        if (wrapped) ptx::mbar_wait_spin(&pv_done[sb], sph ^ 1);
+                        if (wrapped) wait_sp(&pv_done[sb], sph ^ 1, 32);
                         ptx::tc_fence_after();
                         const uint64_t a0 = q_desc0 + static_cast<uint64_t>((buf * L::kQBytes) >> 4);
                         const uint32_t d = tmem_base + sb * BKV;
@@ -629,11 +652,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                 const uint64_t b = b0 + static_cast<uint64_t>(((ks >> 2) * (BKV * 128) + (ks & 3) * 32) >> 4);
                                 ptx::mma_bf16_ss(d, a, b, idesc_s, ks != 0 ? 1u : 0u);
                             }
-                            ptx::mma_commit(&s_full[sb]);
+                            ptx::mma_commit(&s_full[tt * kNSB + sel2(tt, t_slot)]);
                             if (last_of_block) ptx::mma_commit(&k_empty[kst]);  // K tile free once the S MMAs of both tiles retire
                             if (last_of_tile) ptx::mma_commit(&q_empty[buf]);   // last S of this tile in the item
                         }
                         __syncwarp();
+                        if (tt != 0) {
+                            if (++t_slot[1] == kNSB) t_slot[1] = 0;
+                        } else {
+                            if (++t_slot[0] == kNSB) t_slot[0] = 0;
+                        }
                         if (tracing) trace_ev(args.trace, 3, n_tr, 12, gs);
                         if (last_of_block) {
                             if (++kst == KS) { kst = 0; kph ^= 1; }

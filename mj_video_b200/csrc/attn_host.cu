@@ -25,11 +25,11 @@ static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
     return 0;
 }
 
-template <int HD, bool CAUSAL>
+template <int HD, bool CAUSAL, bool DBG = false>
 static int launch_attn2_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& a,
                           dim3 grid, cudaStream_t stream, double work) {
     using L = attn2::Smem<HD>;
-    auto kfn = attention2_kernel<HD, CAUSAL>;
+    auto kfn = attention2_kernel<HD, CAUSAL, DBG>;
     static bool configured = false;
     if (!configured) {
         MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -126,6 +126,10 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
         a.n_items = (int)n2;
         a.n_qblocks = n_qblocks;
         dim3 grid2((unsigned)(n2 < sm_count() ? n2 : sm_count()), 1, 1);
+        if (a.trace != nullptr) {  // tools: the debug instantiations exist for the two bench shapes only
+            if (hd == 64 && !d.causal) return launch_attn2_t<64, false, true>(tq, tk, tv, a, grid2, stream, work);
+            if (hd == 128 && d.causal) return launch_attn2_t<128, true, true>(tq, tk, tv, a, grid2, stream, work);
+        }
         if (hd == 64) {
             if (d.causal) return launch_attn2_t<64, true>(tq, tk, tv, a, grid2, stream, work);
             return launch_attn2_t<64, false>(tq, tk, tv, a, grid2, stream, work);

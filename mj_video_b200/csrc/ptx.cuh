@@ -98,6 +98,33 @@ __device__ __forceinline__ void mbar_wait_nocall(uint64_t* bar, uint32_t parity)
     }
 }
 
+// Debug wait (tools/attn_trace.py): like mbar_wait_nocall, but a tripped watchdog first records {code, parity, block,
+// thread} at rec[0..3] - rec points into pinned HOST memory, so the record survives the trap that kills the context.
+__device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, long long* rec, int code, long long aux = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = 0;
+    uint32_t spins = 0;
+    bool recorded = false;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0xffu) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > (MJV_WATCHDOG_CYCLES / 8)) {
+                if (!recorded && rec != nullptr) {  // record, then keep waiting so that the other roles record too
+                    rec[0] = code;
+                    rec[1] = parity;
+                    rec[2] = blockIdx.x;
+                    rec[3] = threadIdx.x;
+                    rec[4] = aux;
+                    __threadfence_system();
+                    recorded = true;
+                }
+                if (now - t0 > (MJV_WATCHDOG_CYCLES / 4)) __trap();
+            }
+        }
+    }
+}
+
 // Bare spin (three instructions). For roles whose stall is always also seen by a watchdog-carrying waiter of the same
 // CTA (attention2: every hand-off cycle passes through the softmax warps' s_full wait), and whose instruction footprint
 // matters more than a second watchdog.

@@ -48,7 +48,7 @@ def run_llm(lens=None, H=16, Hkv=8, hd=128):
 
 
 def summarize(buf, name):
-    ev = buf.view(4, EV, 2).cpu().numpy()
+    ev = buf.view(4, EV, 2).cpu().numpy().copy()
     res = {}
     for role in (0, 1):
         e = ev[role]
@@ -86,20 +86,36 @@ def summarize(buf, name):
     return res
 
 
+CODES = {1: "softmax s_full", 2: "softmax pv_done (rescale)", 3: "softmax o_empty", 4: "epilogue l_ready", 5: "epilogue o_done",
+         10: "tma q_empty", 11: "tma k_empty", 12: "tma v_empty", 20: "pv v_full", 21: "pv o_empty", 22: "pv p_full",
+         30: "s q_full", 31: "s k_full", 32: "s pv_done"}
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["vit", "llm"]
     out = {}
     for w in which:
         fn = run_vit() if w == "vit" else run_llm()
-        fn()
-        torch.cuda.synchronize()
-        buf = torch.zeros(4 * EV * 2, dtype=torch.int64, device=dev)
+        # pinned HOST buffer (device-visible under UVA): records written before a watchdog trap survive the dead context
+        buf = torch.zeros(4 * EV * 2 + 16 * 8, dtype=torch.int64).pin_memory()
         os.environ["MJV_ATTN_TRACE"] = hex(buf.data_ptr())
-        fn()
-        torch.cuda.synchronize()
+        try:
+            fn()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(w, "FAILED:", repr(e)[:120])
+            rec = buf[4 * EV * 2:].view(16, 8).numpy()
+            for wi in range(16):
+                if rec[wi, 0] != 0:
+                    print(f"  warp {wi}: wedged in '{CODES.get(int(rec[wi, 0]), rec[wi, 0])}' parity {rec[wi, 1]} block {rec[wi, 2]} "
+                          f"thread {rec[wi, 3]} aux item {rec[wi, 4] >> 32} low {hex(int(rec[wi, 4] & 0xffffffff))}")
+            raw = buf[:4 * EV * 2].view(4, EV, 2).numpy()
+            for role in range(4):
+                n = int((raw[role, :, 0] != 0).sum())
+                last = raw[role, max(0, n - 3):n]
+                print(f"  role {role}: {n} events, last: {[(int(c), int(x >> 32), int(x & 0xffffffff)) for c, x in last]}")
+            sys.exit(1)
         os.environ.pop("MJV_ATTN_TRACE")
-        out[w] = summarize(buf, w)
-        raw = buf.view(4, EV, 2).cpu().numpy()
-        np.save(f"gpurun_out/attn_trace_{w}.npy", raw)
+        out[w] = summarize(buf[:4 * EV * 2].clone(), w)
+        np.save(f"gpurun_out/attn_trace_{w}.npy", buf[:4 * EV * 2].view(4, EV, 2).numpy())
     with open("gpurun_out/attn_trace.json", "w") as f:
         json.dump(out, f, indent=1)

@@ -343,22 +343,35 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     const int pch = (((valid + 15) >> 4) + 1) >> 1;     // chunks the P·V MMA reads (16-column k-steps)
                     if (warp_has_rows) {
                         uint32_t v[128];
-                        ptx::tmem_ld_x32(tmem_S, v);
-                        if (nch > 1) ptx::tmem_ld_x32(tmem_S + 32, v + 32);
-                        if (nch > 2) ptx::tmem_ld_x32(tmem_S + 64, v + 64);
-                        if (nch > 3) ptx::tmem_ld_x32(tmem_S + 96, v + 96);
-                        ptx::tmem_wait_ld();
-                        if (!full) {
+                        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                        if (full) {
+                            // fast path, straight-line: the second half of the row is still in flight while the maximum of
+                            // the first half is taken
+                            ptx::tmem_ld_x32(tmem_S, v);
+                            ptx::tmem_ld_x32(tmem_S + 32, v + 32);
+                            ptx::tmem_wait_ld();
+                            ptx::tmem_ld_x32(tmem_S + 64, v + 64);
+                            ptx::tmem_ld_x32(tmem_S + 96, v + 96);
+                            max_chunk<0>(v, mx);
+                            max_chunk<1>(v, mx);
+                            ptx::tmem_wait_ld();
+                            max_chunk<2>(v, mx);
+                            max_chunk<3>(v, mx);
+                        } else {
+                            ptx::tmem_ld_x32(tmem_S, v);
+                            if (nch > 1) ptx::tmem_ld_x32(tmem_S + 32, v + 32);
+                            if (nch > 2) ptx::tmem_ld_x32(tmem_S + 64, v + 64);
+                            if (nch > 3) ptx::tmem_ld_x32(tmem_S + 96, v + 96);
+                            ptx::tmem_wait_ld();
                             mask_chunk<0>(v, lim);
                             if (nch > 1) mask_chunk<1>(v, lim);
                             if (nch > 2) mask_chunk<2>(v, lim);
                             if (nch > 3) mask_chunk<3>(v, lim);
+                            max_chunk<0>(v, mx);
+                            if (nch > 1) max_chunk<1>(v, mx);
+                            if (nch > 2) max_chunk<2>(v, mx);
+                            if (nch > 3) max_chunk<3>(v, mx);
                         }
-                        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                        max_chunk<0>(v, mx);
-                        if (nch > 1) max_chunk<1>(v, mx);
-                        if (nch > 2) max_chunk<2>(v, mx);
-                        if (nch > 3) max_chunk<3>(v, mx);
                         const float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2;  // scale > 0
                         // ---- lazy rescale of the TMEM accumulator
                         float alpha = 1.0f;
@@ -399,25 +412,39 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         uint32_t zero16[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) zero16[i] = 0u;
-                        exp_chunk<0>(v, pk, sc2, nm2, ps2);
-                        ptx::tmem_st_x16(tmem_S, pk);
-                        if (nch > 1) {
-                            exp_chunk<1>(v, pk, sc2, nm2, ps2);
-                            ptx::tmem_st_x16(tmem_S + 16, pk);
-                        } else if (pch > 1) {
-                            ptx::tmem_st_x16(tmem_S + 16, zero16);
-                        }
-                        if (nch > 2) {
-                            exp_chunk<2>(v, pk, sc2, nm2, ps2);
-                            ptx::tmem_st_x16(tmem_S + 32, pk);
-                        } else if (pch > 2) {
-                            ptx::tmem_st_x16(tmem_S + 32, zero16);
-                        }
-                        if (nch > 3) {
-                            exp_chunk<3>(v, pk, sc2, nm2, ps2);
-                            ptx::tmem_st_x16(tmem_S + 48, pk);
-                        } else if (pch > 3) {
-                            ptx::tmem_st_x16(tmem_S + 48, zero16);
+                        if (full) {
+                            // one basic block for the whole row: the tail of a chunk (its last pairs wait for the MUFU
+                            // latency, then the store) overlaps the exponentials of the next chunk
+                            uint32_t pk1[16], pk2[16], pk3[16];
+                            exp_chunk<0>(v, pk, sc2, nm2, ps2);
+                            ptx::tmem_st_x16(tmem_S, pk);
+                            exp_chunk<1>(v, pk1, sc2, nm2, ps2);
+                            ptx::tmem_st_x16(tmem_S + 16, pk1);
+                            exp_chunk<2>(v, pk2, sc2, nm2, ps2);
+                            ptx::tmem_st_x16(tmem_S + 32, pk2);
+                            exp_chunk<3>(v, pk3, sc2, nm2, ps2);
+                            ptx::tmem_st_x16(tmem_S + 48, pk3);
+                        } else {
+                            exp_chunk<0>(v, pk, sc2, nm2, ps2);
+                            ptx::tmem_st_x16(tmem_S, pk);
+                            if (nch > 1) {
+                                exp_chunk<1>(v, pk, sc2, nm2, ps2);
+                                ptx::tmem_st_x16(tmem_S + 16, pk);
+                            } else if (pch > 1) {
+                                ptx::tmem_st_x16(tmem_S + 16, zero16);
+                            }
+                            if (nch > 2) {
+                                exp_chunk<2>(v, pk, sc2, nm2, ps2);
+                                ptx::tmem_st_x16(tmem_S + 32, pk);
+                            } else if (pch > 2) {
+                                ptx::tmem_st_x16(tmem_S + 32, zero16);
+                            }
+                            if (nch > 3) {
+                                exp_chunk<3>(v, pk, sc2, nm2, ps2);
+                                ptx::tmem_st_x16(tmem_S + 48, pk);
+                            } else if (pch > 3) {
+                                ptx::tmem_st_x16(tmem_S + 48, zero16);
+                            }
                         }
                         float s0, s1, s2, s3;
                         ptx::unpack_f32x2(ptx::fadd2(ps2[0], ps2[1]), s0, s1);

@@ -11,11 +11,10 @@ static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
                          dim3 grid, cudaStream_t stream, double work) {
     using L = attn_detail::Smem<HD>;
     auto kfn = attention_kernel<HD, CAUSAL>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;  // per instantiation and device
+    if (once.first()) {
         MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
     }
     {
         LaunchScope scope(CAUSAL ? TAG_ATTN_CAUSAL : TAG_ATTN_BIDIR, stream, work);
@@ -30,10 +29,9 @@ static int launch_attn2_t(const CUtensorMap& tq, const CUtensorMap& tk, const CU
                           dim3 grid, cudaStream_t stream, double work) {
     using L = attn2::Smem<HD>;
     auto kfn = attention2_kernel<HD, CAUSAL, DBG>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;  // per instantiation and device
+    if (once.first()) {
         MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        configured = true;
     }
     {
         LaunchScope scope(CAUSAL ? TAG_ATTN_CAUSAL : TAG_ATTN_BIDIR, stream, work);

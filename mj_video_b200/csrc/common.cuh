@@ -96,14 +96,29 @@ inline int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint6
     return make_tmap_bf16(out, base, 2, dims, str, box);
 }
 
-inline int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return n;
+// Process-wide caches are kept PER DEVICE: Engine(device=...) and load_video(device=...) accept any device, and function
+// attributes, SM counts and library-owned device tables all belong to one device.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
+inline int sm_count() {
+    static int n[kMaxDevices] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    return n[dev];
+}
+// `static PerDeviceOnce once; if (once.first()) cudaFuncSetAttribute(...)`: true once per device
+struct PerDeviceOnce {
+    bool done[kMaxDevices] = {};
+    bool first() {
+        const int dev = current_device();
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
 
 }  // namespace mjv

@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include <map>
+#include <tuple>
 #include <mutex>
 #include <vector>
 
@@ -149,12 +150,12 @@ struct DeviceCoeffs {
     int* kk = nullptr;
 };
 
-// geometry cache: coefficient tables depend only on (in,out) per axis. Library-owned device memory, never freed.
+// geometry cache: coefficient tables depend only on (in,out) per axis and are kept per device. Library-owned device memory, never freed.
 int get_device_coeffs(int in_size, int out_size, cudaStream_t st, DeviceCoeffs* out) {
     static std::mutex mu;
-    static std::map<std::pair<int, int>, DeviceCoeffs> cache;
+    static std::map<std::tuple<int, int, int>, DeviceCoeffs> cache;  // (device, in, out): the tables live on one device
     std::lock_guard<std::mutex> lock(mu);
-    auto key = std::make_pair(in_size, out_size);
+    auto key = std::make_tuple(current_device(), in_size, out_size);
     auto it = cache.find(key);
     if (it != cache.end()) {
         *out = it->second;

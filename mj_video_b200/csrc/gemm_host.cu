@@ -12,10 +12,9 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
                          const CUtensorMap& tmO2, const GemmArgs& args, cudaStream_t stream) {
     using L = gemm_detail::SmemLayout<BN, STAGES, CG>;
     auto kfn = gemm_bf16_tn_kernel<BN, EPI, STAGES, CG>;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    static PerDeviceOnce once;  // per instantiation and device
+    if (once.first()) {
         MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        configured = true;
     }
     const int tiles = args.num_m_blocks * args.num_n_blocks;
     const int max_groups = sm_count() / CG;

@@ -369,11 +369,10 @@ int im2col_patches(const void* px, int px_dtype, void* out, int T, int img, int 
     const int kvec = Kpad / 8;
     MJV_CHECK(kvec <= 512, MJV_ERR_ARG, "im2col: Kpad %d too large", Kpad);
     const int threads = kvec * (kvec >= 384 ? 1 : 384 / kvec);  // a multiple of kvec, ~384 threads
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         MJV_CUDA_OK(cudaFuncSetAttribute(im2col_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         MJV_CUDA_OK(cudaFuncSetAttribute(im2col_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
     }
     LaunchScope scope(TAG_IM2COL, st, (double)T * (3.0 * img * img * (px_dtype == MJV_DTYPE_F32 ? 4 : 2) + 2.0 * g_ * g_ * Kpad));
     if (px_dtype == MJV_DTYPE_BF16)

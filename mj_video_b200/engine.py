@@ -269,7 +269,13 @@ class Engine:
         cu = np.zeros(B + 1, dtype=np.int64)
         cu[1:] = np.cumsum(lengths)
         M = int(cu[-1])
-        token_ids = np.concatenate([ids[b, : lengths[b]] for b in range(B)]).astype(np.int32)
+        token_ids = np.concatenate([ids[b, : lengths[b]] for b in range(B)])
+        # nn.Embedding raises IndexError for an id outside the table (e.g. a tokenizer with added tokens beyond
+        # config.vocab_size, modeling_internvl_chat.py:163); the embed kernel would silently leave a stale row instead
+        if token_ids.size and (int(token_ids.min()) < 0 or int(token_ids.max()) >= self.dims.vocab):
+            raise IndexError(f"index out of range in self: token id {int(token_ids.max())} / {int(token_ids.min())} "
+                             f"outside the embedding table of {self.dims.vocab} rows")
+        token_ids = token_ids.astype(np.int32)
         row_pos = np.concatenate([np.arange(lengths[b]) for b in range(B)]).astype(np.int32)
         vt_starts = np.zeros(B, dtype=np.int64)
         off = 0
@@ -333,6 +339,11 @@ class Engine:
         d = self.dims
         if pixel_values.dim() != 4:
             raise ValueError(f"wrong pixel_values size: {tuple(pixel_values.shape)}")  # modeling_intern_vit.py:410-413
+        # the im2col and ViT kernels index every tile with the configured geometry: anything else would read out of
+        # bounds (the reference raises inside nn.Conv2d / the position-embedding add for a wrong channel count or size)
+        if tuple(pixel_values.shape[1:]) != (3, d.image_size, d.image_size):
+            raise ValueError(f"pixel_values must be [tiles, 3, {d.image_size}, {d.image_size}], got "
+                             f"{tuple(pixel_values.shape)}")
         T = int(pixel_values.shape[0])
         meta, info = self.prepare_batch(input_ids, attention_mask, T, pad_token_id, img_context_token_id)
         with torch.cuda.device(self.device):

@@ -152,14 +152,36 @@ class InternVLChatRewardModeling(nn.Module):
         self.config = config
         self._engine: Engine | None = None
         self._engine_key = None
+        # The reference builds the backbone with InternVLChatModel.from_pretrained(name) (moe_reward.py:142): it either
+        # holds the checkpoint's weights or the constructor raises. Here the backbone parameters start as uninitialised
+        # memory (there is no hub offline); every key stays in this set until a load_state_dict delivers it, and forward
+        # refuses to run on a backbone that was never (or only partly) loaded instead of scoring garbage.
+        self._backbone_unloaded = {"model." + k for k, _ in self.model.named_parameters()}
+        self.register_load_state_dict_post_hook(self._note_loaded_keys(""))
+        self.model.register_load_state_dict_post_hook(self._note_loaded_keys("model."))
         if name and os.path.isdir(str(name)):
             self._load_backbone_checkpoint(str(name))
 
+    def _note_loaded_keys(self, prefix: str):
+        def hook(module, incompatible):
+            # the backbone's hook sees keys relative to it when it is loaded directly and absolute ones when the load came
+            # through this module (its own children are vision_model / language_model / mlp1, never "model.")
+            missing = {k if (not prefix or k.startswith(prefix)) else prefix + k for k in incompatible.missing_keys}
+            own = {prefix + k for k, _ in module.named_parameters()}
+            self._backbone_unloaded -= (own - missing)
+        return hook
+
+    def mark_backbone_initialised(self) -> None:
+        """Declare that the backbone parameters were filled in place (not through load_state_dict)."""
+        self._backbone_unloaded.clear()
+
     # ------------------------------------------------------------------ checkpoints (InternVLChatModel.from_pretrained)
     def _load_backbone_checkpoint(self, path: str):
+        """`name` is a local directory: its *.safetensors must hold the complete backbone, as from_pretrained requires
+        (a directory with only *.bin shards, or a partial checkpoint, raises instead of leaving parameters unset)."""
         files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
         if not files:
-            return
+            raise FileNotFoundError(f"no *.safetensors backbone weights under {path}")
         from safetensors.torch import load_file
         sd = {}
         for f in files:
@@ -167,6 +189,8 @@ class InternVLChatRewardModeling(nn.Module):
         missing, unexpected = self.model.load_state_dict(sd, strict=False)
         if unexpected:
             raise RuntimeError(f"unexpected keys in backbone checkpoint: {unexpected[:5]}")
+        if missing:
+            raise RuntimeError(f"backbone checkpoint {path} lacks {len(missing)} tensors, e.g. {missing[:5]}")
 
     # ------------------------------------------------------------------ engine sync
     def _weights_key(self):
@@ -175,6 +199,11 @@ class InternVLChatRewardModeling(nn.Module):
 
     def _get_engine(self) -> Engine:
         dev = self.model.device
+        if self._backbone_unloaded:
+            some = sorted(self._backbone_unloaded)[:3]
+            raise RuntimeError(f"{len(self._backbone_unloaded)} backbone parameters were never loaded (e.g. {some}): load a "
+                               "checkpoint with load_state_dict / a local `name` directory first (the reference's "
+                               "from_pretrained would have loaded them or raised)")
         if dev.type != "cuda":
             raise RuntimeError("InternVLChatRewardModeling (mj_video_b200) needs a CUDA device: call .cuda() first; "
                                "there is no CPU path")

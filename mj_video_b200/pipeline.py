@@ -61,7 +61,7 @@ class PairScorer:
 
     def __init__(self, forward_fn, preprocess_fn, pad_token_id: int, rows_per_step: int = 32, max_num: int = 1,
                  input_size: int = 448, device=None, group=None, prefetch: int = 2, gather_fn=None,
-                 preprocess_batch_fn=None):
+                 preprocess_batch_fn=None, score_width: int | None = None):
         """forward_fn(pixel_values, input_ids, attention_mask) -> [rows, W] fp32 score table on `device`;
         preprocess_fn(frames_u8_device, input_size, max_num) -> (tiles, tiles_per_frame)."""
         if rows_per_step < 2 or rows_per_step % 2:
@@ -72,6 +72,9 @@ class PairScorer:
         self.device = torch.device(device) if device is not None else torch.device("cpu")
         self.group = group
         self.prefetch = max(1, prefetch)
+        # columns of the score table (num_objectives + num_aspects + 1). A rank that owns no pair never sees a forward
+        # result, and its all-gather contribution must still have the same width as everyone else's.
+        self.score_width = score_width
         # (local table, n_pairs) -> full table; default: torch.distributed all-gather (gloo on CPU, NCCL on GPU)
         self.gather_fn = gather_fn or (lambda local, n: mdist.allgather_scores(local, n, group))
         # optional: (list of device uint8 clips) -> all tiles of the micro-batch in ONE buffer (no per-row concat copy)
@@ -108,6 +111,7 @@ class PairScorer:
                 tdist.get_world_size(kw.get("group")) > 1:
             kw["gather_fn"] = mdist.NcclScoreGather(engine.device, kw.get("group")).gather  # C ABI: mjv_allgather_scores
         kw.setdefault("preprocess_batch_fn", pre_batch)
+        kw.setdefault("score_width", engine.dims.num_objectives + engine.dims.num_aspects + 1)
         return cls(fwd, pre, pad_token_id, device=engine.device, **kw)
 
     # ------------------------------------------------------------------------------------------------
@@ -158,7 +162,7 @@ class PairScorer:
             staged = self._stage(nxt, copy_stream)            # overlaps with the forward just enqueued
         th.join()
         if local is None:                                      # this rank owns no pair
-            width = self._width_hint(dataset)
+            width = self.score_width if self.score_width is not None else self._width_hint(dataset)
             local = torch.zeros((0, width), dtype=torch.float32, device=self.device)
         table = self.gather_fn(local, n_pairs)
         return dict(scores=table, prefer=mdist.preference_decisions(table[:, -1]), rows_local=row0)

@@ -135,3 +135,45 @@ def test_pair_scorer_propagates_dataset_errors():
     fwd, pre = _toy_fns()
     with pytest.raises(RuntimeError, match="decode failed"):
         PairScorer(fwd, pre, pad_token_id=2, rows_per_step=2).score(Bad(4))
+
+
+class _NoWidthPairs(_ToyPairs):
+    score_width = None  # a dataset that does not know the table width (only the engine does)
+
+
+def _empty_rank_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mj_video_b200.pipeline import PairScorer
+    _, pre = _toy_fns()
+
+    def fwd7(pv, ids, mask):  # a head with 4 objectives + 2 aspects + 1 score = 7 columns
+        t = torch.zeros((ids.shape[0], 7))
+        t[:, 0], t[:, -1] = ids[:, 1].float(), ids[:, 1].float() * 0.5
+        return t
+    ds = _NoWidthPairs(1)
+    del type(ds).score_width
+    out = PairScorer(fwd7, pre, pad_token_id=2, rows_per_step=2, score_width=7).score(ds)
+    q.put((rank, out["scores"].tolist(), out["rows_local"]))
+    dist.destroy_process_group()
+
+
+def test_pair_scorer_rank_without_pairs_uses_engine_width():
+    """ceil-sharding leaves trailing ranks empty (1 pair on 2 ranks); the empty rank's all-gather contribution
+    must have the engine's table width, not a hard-coded 34, or the collective mismatches and hangs."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_empty_rank_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rows = {rank: n for rank, _, n in got}
+    assert rows == {0: 2, 1: 0}
+    for _, table, _ in got:
+        assert torch.tensor(table).shape == (2, 7)
+        assert [r[0] for r in table] == [5.0, 6.0]

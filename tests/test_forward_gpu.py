@@ -85,6 +85,18 @@ def test_dropin_module_vs_reference_golden(gpu, golden_forward):
         m.forward(pv.to(torch.bfloat16).cuda(), bad.cuda(), mask.cuda())
     with pytest.raises(ValueError, match="wrong pixel_values size"):
         m.forward(pv[0].cuda(), ids.cuda(), mask.cuda())
+    # tiles of another geometry (e.g. load_video(input_size=224)) must not reach the kernels, which index with the
+    # configured image size; an id outside the embedding table raises like nn.Embedding instead of leaving a stale row
+    with pytest.raises(ValueError, match=r"pixel_values must be \[tiles, 3, 448, 448\]"):
+        m.forward(torch.zeros(pv.shape[0], 3, 224, 224, dtype=torch.bfloat16).cuda(), ids.cuda(), mask.cuda())
+    with pytest.raises(ValueError, match="pixel_values must be"):
+        m.forward(torch.zeros(pv.shape[0], 1, 448, 448, dtype=torch.bfloat16).cuda(), ids.cuda(), mask.cuda())
+    oob = ids.clone()
+    oob[0, 3] = d.vocab + 5
+    with pytest.raises(IndexError, match="index out of range"):
+        m.forward(pv.to(torch.bfloat16).cuda(), oob.cuda(), mask.cuda())
+    # ... and the module still scores correctly afterwards
+    _check(m.forward(pv.to(torch.bfloat16).cuda(), ids.cuda(), mask.cuda()), fix["outputs"])
 
 
 @pytest.fixture(scope="module")

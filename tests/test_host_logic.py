@@ -123,11 +123,19 @@ def test_config_and_module_surface():
     m = InternVLChatRewardModeling("unused", cfg)
     sd = synth.make_state_dict(d, seed=1)
     assert set(m.state_dict().keys()) == set(sd.keys())                    # SURVEY §A.2 key space
-    m.load_state_dict(sd, strict=True)
     m.config.pad_token_id = 2
     m.model.img_context_token_id = synth.IMG_CONTEXT
-    assert not m.reward_transform_matrix.requires_grad
     ids, mask = synth.pad_batch([synth.make_input_ids(0, [1] * 8, n_cap=10)])
+    # the reference's from_pretrained(name) loads the backbone or raises (moe_reward.py:142); here a backbone that was never
+    # loaded, or only partly (strict=False with missing keys), must not score uninitialised memory
+    with pytest.raises(RuntimeError, match="never loaded"):
+        m.forward(torch.zeros(8, 3, 448, 448), ids, mask)
+    partial = {k: v for k, v in sd.items() if "vision_model.encoder.layers.0." not in k}
+    m.load_state_dict(partial, strict=False)
+    with pytest.raises(RuntimeError, match=r"backbone parameters were never loaded .*vision_model\.encoder\.layers\.0\."):
+        m.forward(torch.zeros(8, 3, 448, 448), ids, mask)
+    m.load_state_dict(sd, strict=True)
+    assert not m.reward_transform_matrix.requires_grad
     with pytest.raises(RuntimeError, match="CUDA"):                        # no CPU fallback
         m.forward(torch.zeros(8, 3, 448, 448), ids, mask)
     with pytest.raises(AssertionError):                                    # moe_reward.py:153-157

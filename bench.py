@@ -33,6 +33,9 @@ WORKLOADS = {
     ("4b", "pairs8"): "InternViT-300M + Phi-3-mini-shaped LLM (d 3072, 32 layers, 32 heads x 96; reference Llama branch), "
                       "full 28-criterion MoE head, bf16, 32 synthetic pairs per GPU, 8 frames 448^2 (BASELINE configs[4])",
     ("4b", "long16x7"): "config-5 model on config-4 rows",
+    ("2b", "pairs4096"): "MJ-VIDEO-2B bf16, chosen/rejected preference scoring of 4096 synthetic pairs (8192 rows, 8 frames 448^2) "
+                         "sharded over the GPUs, micro-batches of 32 rows through pipeline.PairScorer, ONE all-gather "
+                         "(BASELINE configs[2]; strong scaling)",
 }
 
 
@@ -175,6 +178,83 @@ def run_reference(args):
     print(json.dumps(line), file=_OUT, flush=True)
 
 
+def run_pairs(args):
+    """--workload pairs4096 (BASELINE configs[2]): the whole job through the public pipeline (reference loop:
+    scripts/eval/eval_genai_mjvideo.py:125-163, decision rule overall_train.py:427) - host collation of ragged prompts,
+    pinned H2D of uint8 clips on a copy stream, frame kernels, forward, and ONE all-gather of the score table. STRONG
+    scaling: the total number of pairs is fixed, every rank scores a contiguous block with chosen/rejected co-located.
+    The timed region is the wall clock of scorer.score() between barriers (max over ranks): there is no device-resident
+    variant of a data-loading job, so `value` and `e2e` are the same measurement."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from mj_video_b200 import _lib, synth
+    from mj_video_b200.engine import Engine, EngineDims
+    from mj_video_b200.pipeline import PairScorer, SyntheticPairs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    lib = _lib.load()
+    d = model_dims(args.model)
+    eng = Engine(EngineDims.from_synth(d), dev)
+    eng.load_state_dict(synth.make_state_dict(d, seed=1234, include_lm_head=False))
+    scorer = PairScorer.for_engine(eng, synth.PAD, synth.IMG_CONTEXT, rows_per_step=args.batch)
+    n_pairs = args.pairs
+    data = SyntheticPairs(n_pairs, pool=args.pool)          # `pool` distinct clips, generated before the timed region
+    warm = SyntheticPairs(min(n_pairs, world * args.batch * max(1, args.warmup) // 2))
+    warm.pool = data.pool
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    scorer.score(warm)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib.mjv_reset_launch_count()
+    t0 = time.perf_counter()
+    out = scorer.score(data)
+    barrier()
+    el = time.perf_counter() - t0
+    launches = int(lib.mjv_launch_count())
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([el], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el = t.item()
+    if rank == 0:
+        table = out["scores"].cpu()
+        margin = (table[:, -1].view(-1, 2)[:, 0] - table[:, -1].view(-1, 2)[:, 1]).abs()
+        rows = 2 * n_pairs
+        steps = -(-rows // (world * args.batch))
+        h2d = rows * 8 * 448 * 448 * 3 // steps
+        line = dict(metric=METRIC, value=rows / el, unit=UNIT, n_gpus=world, steps=steps, warmup=args.warmup,
+                    ms_per_step=el / steps * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
+                    data="synthetic",
+                    config=dict(workload=WORKLOADS[(args.model, "pairs4096")], preference_pairs=n_pairs, rows=rows,
+                                rows_per_micro_batch=args.batch, distinct_clips=args.pool,
+                                l2="every micro-batch streams 0.15 GB of uint8 frames and >5 GB of activations (L2 is 126 MB)",
+                                parallelism=f"dp{world}: contiguous pair blocks, chosen/rejected on one rank, 1 all-gather"),
+                    e2e=dict(value=rows / el, unit=UNIT, h2d_bytes_per_step=int(h2d),
+                             d2h_bytes_per_step=int(table.numel() * 4 // steps)),
+                    preference_pairs_per_s=n_pairs / el, seconds=el, gpu_launches=launches, clocks=clocks,
+                    decisions_sha256=hashlib.sha256(out["prefer"].cpu().numpy().tobytes()).hexdigest(),
+                    scores_sha256=hashlib.sha256(table.numpy().tobytes()).hexdigest(),
+                    prefer_video1_frac=float(out["prefer"].float().mean()), mean_abs_margin=float(margin.mean()),
+                    roofline=None, cpu_baseline=None)
+        print(json.dumps(line), file=_OUT, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_mjv(args):
     import numpy as np
     import torch
@@ -259,12 +339,15 @@ def run_mjv(args):
     recs = _lib.profile_collect()
     value = world * B * args.steps / (ms * 1e-3)
 
-    # dominant kernel: the fused gate/up SwiGLU GEMM (27% of the algorithmic FLOPs)
+    # dominant kernel: the fused gate/up SwiGLU GEMM (27% of the algorithmic FLOPs).
+    # Rate = sum(FLOPs) / sum(time) over its full-size launches only: 1 launch in 24 is the last decoder layer's shortcut on
+    # the 2*B gathered rows (M = 64, ~0.03 ms), and a plain average over launches would overstate the rate by ~4 %.
     M_tokens = sum(lengths)
-    k_ms = [r[1] for r in recs if r[0] == "gemm_swiglu"]
     k_flops = 2.0 * M_tokens * (2 * d.llm_inter) * d.llm_hidden
-    avg_ms = sum(k_ms) / max(1, len(k_ms))
-    achieved = k_flops / (avg_ms * 1e-3) / 1e12 if k_ms else None
+    big = [(t_ms, w) for name, t_ms, w in recs if name == "gemm_swiglu" and w >= 0.5 * k_flops]
+    sum_ms = sum(t for t, _ in big)
+    achieved = sum(w for _, w in big) / (sum_ms * 1e-3) / 1e12 if big else None
+    avg_ms = sum_ms / max(1, len(big))
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")) as f:
@@ -274,8 +357,10 @@ def run_mjv(args):
     roofline = dict(bound="tensor", kernel="gemm_bf16_tn_kernel<256,EPI_SWIGLU,4> (LLM w1|w3 + SiLU*mul)",
                     achieved=achieved, peak=pk["sustained"], unit="TFLOP/s",
                     frac=(achieved / pk["sustained"]) if achieved else None, traffic=traffic,
+                    traffic_source="profiles/ncu_dominant_kernel.json (one ncu --set full capture of this kernel, per launch)",
                     peak_source=f"{pk['src']} sustained bf16 (kernel timed inside a long step); burst {pk['burst']}",
-                    launches_timed=len(k_ms), avg_launch_ms=avg_ms, flops_per_launch=k_flops)
+                    launches_timed=len(big), launches_excluded=len([1 for n, _, _ in recs if n == "gemm_swiglu"]) - len(big),
+                    avg_launch_ms=avg_ms, flops_per_launch=k_flops)
 
     # whole-step algorithmic FLOPs -> end-to-end fraction of the tensor roofline
     F_step = step_flops(d, T, lengths)
@@ -310,28 +395,44 @@ def run_mjv(args):
         e2e_s = t.item()
     e2e_val = world * B * args.steps / e2e_s
 
-    # ---------------------------------------------------------------- optional per-kernel breakdown (untimed extra step)
+    # ---------------------------------------------------------------- per-kernel breakdown (one extra, untimed step)
     breakdown = None
-    if args.breakdown and rank == 0:
+    roofline_kernels = None
+    if rank == 0:
         lib.mjv_profile_enable(_lib.tag_mask())
         step_resident()
         torch.cuda.synchronize()
         lib.mjv_profile_enable(0)
-        agg = {}
+        agg, by_tag = {}, {}
         for name, t_ms, work in _lib.profile_collect():
+            tagname = name
             if name.startswith("gemm_"):
                 name = f"{name}[{work / 1e12:.2f}TF]"   # one line per GEMM shape
-            a = agg.setdefault(name, dict(launches=0, ms=0.0, work=0.0))
-            a["launches"] += 1
-            a["ms"] += t_ms
-            a["work"] += work
+            for key, table in ((name, agg), (tagname, by_tag)):
+                a = table.setdefault(key, dict(launches=0, ms=0.0, work=0.0))
+                a["launches"] += 1
+                a["ms"] += t_ms
+                a["work"] += work
         tot = sum(a["ms"] for a in agg.values())
         for a in agg.values():
             a["share"] = a["ms"] / tot
             a["rate_T_per_s"] = a["work"] / (a["ms"] * 1e-3) / 1e12 if a["ms"] > 0 else None
         breakdown = dict(total_kernel_ms=tot, kernels=agg)
-        with open(args.breakdown, "w") as f:
-            json.dump(breakdown, f, indent=1)
+        if args.breakdown:
+            with open(args.breakdown, "w") as f:
+                json.dump(breakdown, f, indent=1)
+        # in-step rate of every kernel family against its own roofline (work = FLOPs for GEMM / attention, bytes otherwise)
+        roofline_kernels = []
+        for tagname, a in sorted(by_tag.items(), key=lambda kv: -kv[1]["ms"]):
+            if a["ms"] <= 0 or a["work"] <= 0:
+                continue
+            tensor = tagname.startswith("gemm_") or tagname.startswith("attn_")
+            rate = a["work"] / (a["ms"] * 1e-3) / 1e12
+            roofline_kernels.append(dict(
+                kernel=tagname, bound="tensor" if tensor else "hbm", launches=a["launches"], ms_per_step=round(a["ms"], 3),
+                share_of_step=round(a["ms"] / tot, 4), achieved=round(rate if tensor else rate * 1e3, 1),
+                unit="TFLOP/s" if tensor else "GB/s",
+                frac=round(rate / pk["sustained"] if tensor else rate * 1e3 / pk["hbm"], 3)))
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     cpu_baseline = None
@@ -341,8 +442,9 @@ def run_mjv(args):
         sd_full = synth.make_state_dict(d2, seed=1234, include_lm_head=True)
         secs = cpu_forward_seconds(d2, sd_full, cores)
         cpu_baseline = dict(value=1.0 / secs, unit=UNIT, cores=cores, kind="port",
-                            sample=f"1 row (BASELINE configs[0]: 8 frames 448^2, fp32, eager attention, incl. the "
-                                   f"reference's unused LM-head matmul), one forward = {secs:.1f} s on {cores} threads")
+                            sample=f"1 row (BASELINE configs[0]: 8 frames 448^2, fp32, eager attention; the reference's LM-head "
+                                   f"matmul, whose logits nobody reads, is NOT computed by the port: about -6 % FLOPs in "
+                                   f"the CPU's favour), one forward = {secs:.1f} s on {cores} threads")
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -352,7 +454,8 @@ def run_mjv(args):
                                 l2="inputs and activations per step (0.15 GB uint8 frames, >5 GB activations) exceed the 126 MB L2",
                                 parallelism=f"dp{world} over preference pairs (chosen/rejected on one rank) + 1 all-gather"),
                     e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
-                    gpu_launches=launches, clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline,
+                    gpu_launches=launches, clocks=clocks, roofline=roofline, roofline_kernels=roofline_kernels,
+                    cpu_baseline=cpu_baseline,
                     step_tflops=step_tflops, step_frac_of_sustained_peak=step_tflops / world / pk["sustained"])
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
@@ -378,7 +481,10 @@ def main():
     ap.add_argument("--impl", default="mjv", choices=["mjv", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="rows (text-video pairs) per GPU per step (default 32; 2 for long16x7)")
     ap.add_argument("--model", default="2b", choices=["2b", "4b"], help="2b = MJ-VIDEO-2B (BASELINE configs[0-3]); 4b = configs[4] shapes")
-    ap.add_argument("--workload", default="pairs8", choices=["pairs8", "long16x7"], help="pairs8 = configs[1]; long16x7 = configs[3]")
+    ap.add_argument("--workload", default="pairs8", choices=["pairs8", "long16x7", "pairs4096"],
+                    help="pairs8 = configs[1]; long16x7 = configs[3]; pairs4096 = configs[2] (whole job, strong scaling)")
+    ap.add_argument("--pairs", type=int, default=4096, help="pairs4096: number of preference pairs of the job")
+    ap.add_argument("--pool", type=int, default=64, help="pairs4096: distinct synthetic clips (generated before timing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write a per-kernel time breakdown JSON here (rank 0)")
     args = ap.parse_args()
@@ -394,7 +500,10 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"), __file__] + sys.argv[1:]
             sys.exit(subprocess.call(cmd, stdout=_OUT))
-        run_mjv(args)
+        if args.workload == "pairs4096":
+            run_pairs(args)
+        else:
+            run_mjv(args)
 
 
 if __name__ == "__main__":

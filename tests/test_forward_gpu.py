@@ -176,7 +176,9 @@ def test_forward_vs_oracle_batch_ragged(tiny_engine, gpu):
 
 
 def test_preference_decisions_tiny(tiny_engine, gpu):
-    """chosen/rejected decisions `~(s0 > s1)` (overall_train.py:427) agree with the fp32 oracle on >= 99.5 % of pairs."""
+    """chosen/rejected decisions `~(s0 > s1)` (overall_train.py:427) on the tiny model vs the fp32 oracle: every pair whose
+    reference margin clears the bf16 noise floor decides identically (the full-size gate with its margin histogram and the
+    three-way drift triangle is tests/test_decisions_gpu.py)."""
     from mj_video_b200 import synth
     from mj_video_b200.data_processor import load_video
     from mj_video_b200.dist import preference_decisions

@@ -189,6 +189,13 @@ typedef struct mjv_config {
     int32_t group_offsets[33]; /* aspect2criteria in dict order: items of aspect a are                      */
     int32_t group_items[32];   /*   group_items[group_offsets[a] .. group_offsets[a+1])                     */
     int32_t ps_version;        /* pixel-shuffle layout: 0 or 2 = 'v2', 1 = 'v1' (modeling_internvl_chat.py:237-241)   */
+    int32_t precision;         /* 0 = bf16 product path (tcgen05 kernels, fp32 accumulation);
+                                  1 = fp32 VERIFICATION mode: every weight and activation in fp32, one plain fp32 CUDA
+                                  kernel per reference op (csrc/engine_fp32.cuh) - what a float32
+                                  InternVLChatRewardModeling computes (moe_reward.py:183-297), gate 1e-4 abs. In this mode
+                                  pixel_values may be fp32 or bf16, mjv_outputs.hidden_state / prompt_embedding are
+                                  fp32 [B, D], mjv_gating_forward takes and returns fp32, and the bf16-only primitives
+                                  and stage entry points return MJV_ERR_STATE.                                          */
 } mjv_config;
 
 int mjv_create(const mjv_config* cfg, mjv_handle** out);

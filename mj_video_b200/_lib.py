@@ -60,7 +60,7 @@ class Config(C.Structure):
         ("num_objectives", C.c_int32), ("num_aspects", C.c_int32), ("gating_hidden", C.c_int32),
         ("gating_n_hidden", C.c_int32), ("gating_temperature", C.c_float),
         ("group_offsets", C.c_int32 * 33), ("group_items", C.c_int32 * 32),
-        ("ps_version", C.c_int32),
+        ("ps_version", C.c_int32), ("precision", C.c_int32),
     ]
 
 

@@ -43,6 +43,7 @@ struct GateW {
 struct mjv_handle {
     mjv_config cfg;
     std::unordered_map<std::string, mjv::Tensor> weights;
+    std::unordered_map<std::string, mjv::Tensor> weights32;  // precision == 1: fp32 copies in the reference's own layouts
     bool finalized = false;
     int kpad = 0;
     // resolved pointers
@@ -81,6 +82,10 @@ struct Arena {
     if (var == nullptr)                                                                                      \
         return set_error(MJV_ERR_NOMEM, "workspace too small: need %zu more bytes at %s:%d", (size_t)(bytes), \
                          __FILE__, __LINE__)
+
+// fp32 verification mode (engine_fp32.cuh, included further down once Dims / al exist)
+int load_weight_f32(mjv_handle* h, const std::string& key, const void* data, long long rows, long long cols, int dtype);
+int finalize_f32(mjv_handle* h);
 
 // ------------------------------------------------------------------------------------------------ weight ingestion
 __global__ void convert_rows_kernel(const void* __restrict__ src, int src_dtype, long long rows, long long cols,
@@ -192,6 +197,7 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
     if (ends_with(key, "language_model.output.weight")) return 0;  // LM head: never used by the reward path
     const long long n_elem = rows * cols;
     h->finalized = false;
+    if (c.precision == 1) return load_weight_f32(h, key, data, rows, cols, dtype);  // verification mode: no re-packing
 
     // rope tables stay fp32
     if (key == "rope.cos" || key == "rope.sin") {
@@ -313,6 +319,7 @@ int need(mjv_handle* h, const std::string& key, const void** out, long long rows
 
 int finalize(mjv_handle* h) {
     const mjv_config& c = h->cfg;
+    if (c.precision == 1) return finalize_f32(h);
     const std::string v = "model.vision_model.";
     MJV_PROPAGATE(need(h, v + "embeddings.class_embedding", &h->cls));
     MJV_PROPAGATE(need(h, v + "embeddings.position_embedding", &h->pos));
@@ -416,6 +423,12 @@ Dims dims_of(const mjv_handle* h) {
     return d;
 }
 inline size_t al(size_t bytes) { return (bytes + 1023) & ~size_t(1023); }
+
+}  // namespace
+}  // namespace mjv
+#include "engine_fp32.cuh"
+namespace mjv {
+namespace {
 
 size_t vit_temp_bytes(const Dims& d, long long T) {
     const size_t Mv = static_cast<size_t>(T) * d.S;
@@ -843,6 +856,7 @@ extern "C" int mjv_create(const mjv_config* cfg, mjv_handle** out) {
 extern "C" void mjv_destroy(mjv_handle* h) {
     if (!h) return;
     for (auto& kv : h->weights) cudaFree(kv.second.ptr);
+    for (auto& kv : h->weights32) cudaFree(kv.second.ptr);
     cudaFree(h->group_offsets_dev);
     cudaFree(h->group_items_dev);
     delete h;
@@ -860,6 +874,7 @@ extern "C" int mjv_finalize_weights(mjv_handle* h) {
 
 extern "C" int64_t mjv_workspace_bytes(const mjv_handle* h, int32_t n_rows, int32_t n_tiles, int64_t n_tokens) {
     if (!h) return -1;
+    if (h->cfg.precision == 1) return static_cast<int64_t>(workspace_bytes_f32(h, n_rows, n_tiles, n_tokens));
     const Dims d = dims_of(h);
     const long long vt_cols = n_tokens + 8LL * n_rows;
     size_t persistent = al(static_cast<size_t>(n_tiles) * d.S * d.C * 2) + al(static_cast<size_t>(n_tokens) * d.D * 2) +
@@ -879,12 +894,24 @@ extern "C" int mjv_gating_forward(mjv_handle* h, int32_t which, const void* x, i
     MJV_PROPAGATE(check_ready(h));
     MJV_CHECK(x != nullptr && out != nullptr && n_rows >= 0, MJV_ERR_ARG, "mjv_gating_forward: bad arguments");
     Arena ar(workspace, static_cast<size_t>(workspace_bytes));
+    if (h->cfg.precision == 1) {  // fp32 in, fp32 out
+        const int n_out = which == 0 ? h->cfg.num_aspects : h->cfg.num_objectives;
+        const char* name = which == 0 ? "aspect_gating" : "criteria_gating";
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (!with_softmax) return gating_logits_f32(h, name, static_cast<const float*>(x), n_rows, n_out, static_cast<float*>(out), ar, st);
+        MJV_ALLOC(logits, float*, ar, static_cast<size_t>(n_rows) * 64 * 4 + 16);
+        MJV_PROPAGATE(gating_logits_f32(h, name, static_cast<const float*>(x), n_rows, n_out, logits, ar, st));
+        const float* ls;
+        MJV_PROPAGATE(need32(h, std::string(name) + ".logit_scale", &ls));
+        return f32::gating_softmax(logits, n_out, h->cfg.gating_temperature, ls, static_cast<float*>(out), n_rows, st);
+    }
     return gating_forward(h, which, x, n_rows, with_softmax, out, ar, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mjv_vit_forward(mjv_handle* h, const void* pixel_values, int32_t pixel_dtype, int32_t n_tiles,
                                void* vit_hidden, void* workspace, int64_t workspace_bytes, void* stream) {
     MJV_PROPAGATE(check_ready(h));
+    MJV_CHECK(h->cfg.precision == 0, MJV_ERR_STATE, "stage entry points are bf16-only: a handle in fp32 verification mode runs through mjv_score_forward");
     if (n_tiles == 0) return 0;
     Arena ar(workspace, static_cast<size_t>(workspace_bytes));
     return vit_forward(h, pixel_values, pixel_dtype, n_tiles, vit_hidden, ar, static_cast<cudaStream_t>(stream));
@@ -893,6 +920,7 @@ extern "C" int mjv_vit_forward(mjv_handle* h, const void* pixel_values, int32_t 
 extern "C" int mjv_project_and_splice(mjv_handle* h, const void* vit_hidden, const mjv_batch* batch, void* embeds,
                                       void* workspace, int64_t workspace_bytes, void* stream) {
     MJV_PROPAGATE(check_ready(h));
+    MJV_CHECK(h->cfg.precision == 0, MJV_ERR_STATE, "stage entry points are bf16-only: a handle in fp32 verification mode runs through mjv_score_forward");
     MJV_CHECK(batch != nullptr, MJV_ERR_ARG, "null batch");
     Arena ar(workspace, static_cast<size_t>(workspace_bytes));
     return project_and_splice(h, vit_hidden, *batch, embeds, ar, static_cast<cudaStream_t>(stream));
@@ -901,6 +929,7 @@ extern "C" int mjv_project_and_splice(mjv_handle* h, const void* vit_hidden, con
 extern "C" int mjv_llm_prefill(mjv_handle* h, void* embeds_inout, const mjv_batch* batch, void* gathered_2b,
                                void* workspace, int64_t workspace_bytes, void* stream) {
     MJV_PROPAGATE(check_ready(h));
+    MJV_CHECK(h->cfg.precision == 0, MJV_ERR_STATE, "stage entry points are bf16-only: a handle in fp32 verification mode runs through mjv_score_forward");
     MJV_CHECK(batch != nullptr, MJV_ERR_ARG, "null batch");
     Arena ar(workspace, static_cast<size_t>(workspace_bytes));
     return llm_prefill(h, embeds_inout, *batch, gathered_2b, ar, static_cast<cudaStream_t>(stream));
@@ -909,6 +938,7 @@ extern "C" int mjv_llm_prefill(mjv_handle* h, void* embeds_inout, const mjv_batc
 extern "C" int mjv_reward_head(mjv_handle* h, const void* gathered_2b, int32_t n_rows, const mjv_outputs* out,
                                void* workspace, int64_t workspace_bytes, void* stream) {
     MJV_PROPAGATE(check_ready(h));
+    MJV_CHECK(h->cfg.precision == 0, MJV_ERR_STATE, "stage entry points are bf16-only: a handle in fp32 verification mode runs through mjv_score_forward");
     MJV_CHECK(out != nullptr, MJV_ERR_ARG, "null outputs");
     Arena ar(workspace, static_cast<size_t>(workspace_bytes));
     return reward_head(h, gathered_2b, n_rows, *out, ar, static_cast<cudaStream_t>(stream));
@@ -922,6 +952,7 @@ extern "C" int mjv_score_forward(mjv_handle* h, const mjv_batch* batch, const mj
     const Dims d = dims_of(h);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar(workspace, static_cast<size_t>(workspace_bytes));
+    if (h->cfg.precision == 1) return score_forward_f32(h, *batch, *out, ar, st);
     MJV_ALLOC(vit_hidden, __nv_bfloat16*, ar, static_cast<size_t>(batch->n_tiles) * d.S * d.C * 2 + 16);
     MJV_ALLOC(embeds, __nv_bfloat16*, ar, static_cast<size_t>(batch->n_tokens) * d.D * 2);
     MJV_ALLOC(gathered, __nv_bfloat16*, ar, 2ULL * batch->n_rows * d.D * 2);

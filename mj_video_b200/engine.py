@@ -134,10 +134,18 @@ _DTYPES = {torch.float32: _lib.MJV_DTYPE_F32, torch.bfloat16: _lib.MJV_DTYPE_BF1
 class Engine:
     """One model on one CUDA device. Not thread-safe (like the reference nn.Module)."""
 
-    def __init__(self, dims: EngineDims, device: torch.device | str = "cuda", rope_inv_freq_bf16: bool = True):
+    def __init__(self, dims: EngineDims, device: torch.device | str = "cuda", rope_inv_freq_bf16: bool = True,
+                 precision: str = "bf16"):
+        """precision: "bf16" = the product path (tcgen05 kernels, fp32 accumulation); "fp32" = the verification mode of
+        north_star ("1e-4 in fp32"): every weight and activation in fp32, one plain CUDA kernel per reference op
+        (csrc/engine_fp32.cuh) - what a float32 InternVLChatRewardModeling computes (moe_reward.py:183-297)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
         self.lib = _lib.load()
         self.dims = dims
-        self.rope_inv_freq_bf16 = rope_inv_freq_bf16
+        self.precision = precision
+        self.fp32 = precision == "fp32"
+        self.rope_inv_freq_bf16 = rope_inv_freq_bf16 and not self.fp32
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.MjvError("mj_video_b200 runs on CUDA devices only (no CPU fallback)")
@@ -149,6 +157,7 @@ class Engine:
                   "mlp1_eps", "num_objectives", "num_aspects", "gating_hidden", "gating_n_hidden",
                   "gating_temperature", "ps_version"):
             setattr(cfg, f, getattr(dims, f))
+        cfg.precision = 1 if self.fp32 else 0
         off = 0
         for a, (_, items) in enumerate(dims.aspect2criteria.items()):
             cfg.group_offsets[a] = off
@@ -208,8 +217,12 @@ class Engine:
         freqs = torch.einsum("i,j->ij", t, inv_freq)
         cos = torch.ones((rows, 64), dtype=torch.float32)
         sin = torch.zeros((rows, 64), dtype=torch.float32)
-        cos[:, : hd // 2] = freqs.cos().to(torch.bfloat16).to(torch.float32)
-        sin[:, : hd // 2] = freqs.sin().to(torch.bfloat16).to(torch.float32)
+        if self.fp32:   # a float32 model keeps the tables as computed (modeling_internlm2.py:166-170 casts to the model dtype)
+            cos[:, : hd // 2] = freqs.cos()
+            sin[:, : hd // 2] = freqs.sin()
+        else:
+            cos[:, : hd // 2] = freqs.cos().to(torch.bfloat16).to(torch.float32)
+            sin[:, : hd // 2] = freqs.sin().to(torch.bfloat16).to(torch.float32)
         self.load_weight("rope.cos", cos)
         self.load_weight("rope.sin", sin)
         self._rope_rows = rows
@@ -359,8 +372,9 @@ class Engine:
             sb.px, sb.dev_meta = px, dev_meta
             sb.scores = torch.empty((B, NO + NA + 1), dtype=torch.float32, device=self.device)
             sb.extras = torch.empty((B, NO + NA + NO + 1), dtype=torch.float32, device=self.device)
-            sb.hidden = torch.empty((B, D), dtype=torch.bfloat16, device=self.device)
-            sb.prompt = torch.empty((B, D), dtype=torch.bfloat16, device=self.device)
+            act = torch.float32 if self.fp32 else torch.bfloat16
+            sb.hidden = torch.empty((B, D), dtype=act, device=self.device)
+            sb.prompt = torch.empty((B, D), dtype=act, device=self.device)
             base = dev_meta.data_ptr()
             b = _lib.Batch()
             b.n_rows, b.n_tiles, b.n_img_tokens, b.n_work = B, T, info["n_img"], info["n_work"]
@@ -389,9 +403,10 @@ class Engine:
         d = self.dims
         if x.dim() != 2 or x.shape[1] != d.llm_hidden or x.device != self.device:
             raise ValueError(f"gating: expected a [B, {d.llm_hidden}] tensor on {self.device}")
-        xb = x.to(torch.bfloat16).contiguous()
+        act = torch.float32 if self.fp32 else torch.bfloat16
+        xb = x.to(act).contiguous()
         n_out = d.num_aspects if which == 0 else d.num_objectives
-        out = torch.empty((xb.shape[0], n_out), dtype=torch.bfloat16, device=self.device)
+        out = torch.empty((xb.shape[0], n_out), dtype=act, device=self.device)
         with torch.cuda.device(self.device):
             ws = self.workspace(max(1, xb.shape[0]), 0, 0)
             _lib.check(self.lib.mjv_gating_forward(self._handle, which, xb.data_ptr(), xb.shape[0], int(with_softmax),

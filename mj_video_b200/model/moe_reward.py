@@ -208,10 +208,13 @@ class InternVLChatRewardModeling(nn.Module):
             raise RuntimeError("InternVLChatRewardModeling (mj_video_b200) needs a CUDA device: call .cuda() first; "
                                "there is no CPU path")
         key = self._weights_key()
-        if self._engine is None or self._engine.device != dev:
+        # a float32 module computes in fp32, as the reference's would (north_star's 1e-4 verification mode); bf16 / fp16
+        # modules run the bf16 tensor-core path
+        precision = "fp32" if self.model.dtype == torch.float32 else "bf16"
+        if self._engine is None or self._engine.device != dev or self._engine.precision != precision:
             # a bf16 module mirrors the reference's `.to(bfloat16)` Llama branch, whose rotary inv_freq buffer is rounded too
             self._engine = Engine(_engine_dims(self.config), dev,
-                                  rope_inv_freq_bf16=self.model.dtype == torch.bfloat16)
+                                  rope_inv_freq_bf16=self.model.dtype == torch.bfloat16, precision=precision)
             self._engine_key = None
         if self._engine_key != key:
             self._engine.load_state_dict(self.state_dict())

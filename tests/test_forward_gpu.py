@@ -531,7 +531,10 @@ def test_fp32_pixel_values_and_fp32_module(tiny_engine, gpu):
     m.model.img_context_token_id = synth.IMG_CONTEXT
     out = m.forward(pv32.cuda(), ids.cuda(), mask.cuda())
     assert out.rewards.dtype == torch.float32 and out.hidden_state.dtype == torch.float32
-    assert (out.score.cpu() - c[:, -1].cpu()).abs().max().item() < 1e-3
+    # a float32 module computes in fp32 (tests/test_fp32_mode_gpu.py holds its 1e-4 gate); the bf16 engine on the same
+    # pixels stays within the bf16 tolerance of it
+    assert m.engine.precision == "fp32"
+    assert (out.score.cpu() - c[:, -1].cpu()).abs().max().item() < TOL
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])

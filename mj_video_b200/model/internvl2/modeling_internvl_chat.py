@@ -38,24 +38,32 @@ def prepare_chat_input(config, tokenizer, pixel_values, question, generation_con
     image_size = config.force_image_size or config.vision_config.image_size
     patch_size = config.vision_config.patch_size
     num_image_token = int((image_size // patch_size) ** 2 * (config.downsample_ratio ** 2))
-    for num_patches in num_patches_list:
-        image_tokens = IMG_START_TOKEN + IMG_CONTEXT_TOKEN * num_image_token * num_patches + IMG_END_TOKEN
-        query = query.replace('<image>', image_tokens, 1)
+    counts = [num_image_token * num_patches for num_patches in num_patches_list]
 
-    # The expanded prompt is ~30 KB of text for 8 frames; the chosen and the rejected row of a preference pair share it
-    # verbatim (same caption, same tile counts), so the tokenisation of the last few prompts is memoised per tokenizer
-    # (host-side caching only — same inputs, same ids; clones are returned).
-    key = (id(tokenizer), query)
+    def expand(text, n_ctx_of):
+        for i in range(len(num_patches_list)):
+            text = text.replace('<image>', IMG_START_TOKEN + IMG_CONTEXT_TOKEN * n_ctx_of(i) + IMG_END_TOKEN, 1)
+        return text
+
+    # SURVEY §8(f) N3, host-side only. (1) The expanded prompt is ~30 KB of text for 8 frames, nearly all of it the
+    # <IMG_CONTEXT> runs. Special tokens are split off atomically before a tokenizer sees the text between them, so a run of
+    # n <IMG_CONTEXT> tokens yields n copies of one id whatever its neighbours are: the prompt is tokenised with ONE context
+    # token per image and the id is repeated afterwards. This is verified, per tokenizer object, against the full
+    # tokenisation on its first calls (and on every 64th after that); one mismatch switches that tokenizer back to the
+    # reference's full-text call for good. (2) The chosen and the rejected row of a pair share the prompt verbatim: the last
+    # few results are memoised per tokenizer. Both give exactly the ids of modeling_internvl_chat.py:36-89.
+    short = expand(query, lambda i: 1)
+    key = (id(tokenizer), short, tuple(counts))
     hit = _TOKENIZED.get(key)
     if hit is not None and hit[2] is not None and hit[2]() is not tokenizer:
         hit = None  # the id was recycled by another tokenizer object
     if hit is None:
-        model_inputs = tokenizer(query, return_tensors='pt')
+        ids_mask = _tokenize_collapsed(tokenizer, short, counts, IMG_CONTEXT_TOKEN, lambda: expand(query, lambda i: counts[i]))
         try:
             ref = weakref.ref(tokenizer)
         except TypeError:
             ref = None
-        hit = (model_inputs['input_ids'].clone(), model_inputs['attention_mask'].clone(), ref)
+        hit = (ids_mask[0], ids_mask[1], ref)
         if len(_TOKENIZED) >= _TOKENIZED_MAX:
             _TOKENIZED.pop(next(iter(_TOKENIZED)))
         _TOKENIZED[key] = hit
@@ -65,8 +73,46 @@ def prepare_chat_input(config, tokenizer, pixel_values, question, generation_con
     return input_ids, attention_mask
 
 
-_TOKENIZED: dict = {}      # (id(tokenizer), prompt text) -> (input_ids, attention_mask), insertion-ordered, bounded
+_TOKENIZED: dict = {}      # (id(tokenizer), collapsed prompt, counts) -> (input_ids, attention_mask), insertion-ordered, bounded
 _TOKENIZED_MAX = 32
+_COLLAPSE_STATE: dict = {}  # id(tokenizer) -> [weakref | None, calls, trusted]
+_VERIFY_FIRST, _VERIFY_EVERY = 2, 64
+
+
+def _tokenize_collapsed(tokenizer, short, counts, ctx_token, full_text):
+    """ids / mask of the full prompt. Fast path: tokenise `short` (one context token per image) and repeat the context id
+    `counts[i]` times; falls back to tokenizer(full_text()) whenever that cannot be shown to be identical."""
+    def slow():
+        mi = tokenizer(full_text(), return_tensors='pt')
+        return mi['input_ids'].clone(), mi['attention_mask'].clone()
+
+    st = _COLLAPSE_STATE.get(id(tokenizer))
+    if st is not None and st[0] is not None and st[0]() is not tokenizer:
+        st = None
+    if st is None:
+        try:
+            ref = weakref.ref(tokenizer)
+        except TypeError:
+            ref = None
+        st = _COLLAPSE_STATE[id(tokenizer)] = [ref, 0, True]
+    if not st[2] or not counts:
+        return slow()
+    ctx_id = tokenizer.convert_tokens_to_ids(ctx_token)
+    mi = tokenizer(short, return_tensors='pt')
+    ids, mask = mi['input_ids'], mi['attention_mask']
+    pos = (ids[0] == ctx_id).nonzero().flatten()
+    if ids.dim() != 2 or ids.shape[0] != 1 or pos.numel() != len(counts):
+        return slow()  # e.g. the question itself contains the context token: not our case to be clever about
+    rep = torch.ones(ids.shape[1], dtype=torch.long)
+    rep[pos] = torch.tensor(counts, dtype=torch.long)
+    fast = (torch.repeat_interleave(ids[0], rep)[None].clone(), torch.repeat_interleave(mask[0], rep)[None].clone())
+    st[1] += 1
+    if st[1] <= _VERIFY_FIRST or st[1] % _VERIFY_EVERY == 0:
+        ref_ids, ref_mask = slow()
+        if ref_ids.shape != fast[0].shape or not torch.equal(ref_ids, fast[0]) or not torch.equal(ref_mask, fast[1]):
+            st[2] = False  # this tokenizer lets the run interact with its surroundings: never collapse for it again
+            return ref_ids, ref_mask
+    return fast
 
 
 # ------------------------------------------------------------------------------------------------ parameter containers

@@ -192,3 +192,35 @@ def reference_load_video(frames: np.ndarray, **kw):
         return mod.load_video(key, **kw)
     finally:
         _StubVideoReader.registry.pop(key, None)
+
+
+_dataset_mod = None
+
+
+def reference_dataset_module():
+    """scripts/data_processor/dataset.py exec'd unmodified (VideoDataCollator :407-554) with stub `decord` and `boto3`
+    (neither is installed here, and the collator uses neither) and scripts/model on sys.path for `internvl2.conversation`."""
+    global _dataset_mod
+    if _dataset_mod is not None:
+        return _dataset_mod
+    _import_reference()          # puts scripts/model on sys.path, registers the timm stub
+    reference_data_module()      # registers the decord stub
+    if "boto3" not in sys.modules:
+        try:
+            __import__("boto3")
+        except Exception:  # noqa: BLE001
+            b3 = types.ModuleType("boto3")
+            sess = types.ModuleType("boto3.session")
+            sess.Session = object
+            b3.session = sess
+            sys.modules["boto3"] = b3
+            sys.modules["boto3.session"] = sess
+    src_path = os.path.join(REFERENCE_ROOT, "scripts", "data_processor", "dataset.py")
+    with open(src_path) as f:
+        src = f.read()
+    mod = types.ModuleType("reference_dataset")
+    mod.__file__ = src_path
+    mod.__name__ = "reference_dataset"      # the `if __name__ == "__main__"` block must not run
+    exec(compile(src, src_path, "exec"), mod.__dict__)
+    _dataset_mod = mod
+    return mod

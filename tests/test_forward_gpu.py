@@ -565,3 +565,22 @@ def test_forward_fuzz_ragged_shapes(tiny_engine, gpu, seed):
     mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
     ref = port.Oracle(d, sd, dtype=torch.float32, device=gpu).forward(pv.float(), ids, mask)
     _check(mine, ref)
+
+
+def test_reference_collator_padding_convention_gives_identical_bits(tiny_engine, gpu):
+    """the reference's VideoDataCollator pads every row to max_length=3072 (dataset.py:407-469), the pair
+    scorer pads to the batch maximum. Rows are packed before any kernel runs, so both conventions score bit-identically."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    d, sd, eng = tiny_engine
+    pv = torch.cat([load_video(synth.make_video(70 + i), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)[0]
+                    for i in range(3)])
+    rows = [synth.make_input_ids(i, [1] * 8, n_cap=n) for i, n in enumerate([12, 77, 40])]
+    ids, mask = synth.pad_batch(rows)
+    a = eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT)["scores"].clone()
+    ids3072 = torch.full((3, 3072), synth.PAD, dtype=torch.long)
+    mask3072 = torch.zeros((3, 3072), dtype=torch.long)
+    ids3072[:, : ids.shape[1]] = ids
+    mask3072[:, : mask.shape[1]] = mask
+    b = eng.forward(pv, ids3072, mask3072, synth.PAD, synth.IMG_CONTEXT)["scores"]
+    assert torch.equal(a, b)

@@ -309,13 +309,18 @@ def test_prepare_chat_input_memoises_identical_prompts():
     q = "".join(f"Frame{i+1}: <image>\n" for i in range(8)) + "a red kite"
     a_ids, a_mask = prepare_chat_input(cfg, tok, pv, q, {}, num_patches_list=[1] * 8)
     b_ids, b_mask = prepare_chat_input(cfg, tok, pv, q, {}, num_patches_list=[1] * 8)
-    assert Counting.calls == 1 and torch.equal(a_ids, b_ids) and torch.equal(a_mask, b_mask)
+    # the first call of a tokenizer object tokenises twice (collapsed prompt + the full text that verifies it); the repeat
+    # of the same prompt does not tokenise at all
+    first = Counting.calls
+    assert first == 2 and torch.equal(a_ids, b_ids) and torch.equal(a_mask, b_mask)
     assert a_ids.data_ptr() != b_ids.data_ptr()
     a_ids[0, 0] = -5                                   # callers may edit their tensors without poisoning the cache
     c_ids, _ = prepare_chat_input(cfg, tok, pv, q, {}, num_patches_list=[1] * 8)
     assert torch.equal(c_ids, b_ids)
     prepare_chat_input(cfg, tok, pv, q + "!", {}, num_patches_list=[1] * 8)
-    assert Counting.calls == 2
+    assert Counting.calls == first + 2       # a new prompt, still inside the verification window
+    prepare_chat_input(cfg, tok, pv, q + "?", {}, num_patches_list=[1] * 8)
+    assert Counting.calls == first + 3       # trusted now: one short tokenisation per new prompt
 
 
 def test_product_never_imports_the_oracle_or_the_reference():
@@ -357,3 +362,88 @@ def test_plain_c_host_links_against_the_abi(built_lib, tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "grid rc 0: 3 x 2" in res.stdout
+
+
+def _chat_cfg():
+    from mj_video_b200.model import InternVLChatRewardModelingConfig
+    d = synth.dims_tiny()
+    vision = dict(hidden_size=d.vit_hidden, num_attention_heads=d.vit_heads, intermediate_size=d.vit_mlp,
+                  num_hidden_layers=d.vit_layers, image_size=448, patch_size=14, qkv_bias=True, qk_normalization=False,
+                  norm_type="layer_norm", layer_norm_eps=1e-6)
+    llm = dict(architectures=["InternLM2ForCausalLM"], hidden_size=d.llm_hidden, intermediate_size=d.llm_inter,
+               num_hidden_layers=d.llm_layers, num_attention_heads=d.llm_heads, num_key_value_heads=d.llm_kv_heads,
+               vocab_size=d.vocab, rms_norm_eps=1e-5, bias=False, rope_theta=1e6, max_position_embeddings=32768)
+    return InternVLChatRewardModelingConfig(vision_config=vision, llm_config=llm, template="internlm2-chat", ps_version="v2",
+                                            force_image_size=448, num_objectives=28, num_aspects=5,
+                                            aspect2criteria=d.aspect2criteria, gating_hidden_dim=d.gating_hidden)
+
+
+def test_prepare_chat_input_collapsed_context_runs_are_token_identical():
+    """the prompt is tokenised with ONE <IMG_CONTEXT> per image and the id repeated afterwards; the result
+    must equal tokenizer(full prompt) (modeling_internvl_chat.py:36-89), the tokenizer must only ever see the short text
+    once the path is trusted, and a tokenizer for which the shortcut is NOT valid must be detected and left alone."""
+    from oracle.make_golden import StubTokenizer
+    from mj_video_b200.model import prepare_chat_input
+    import mj_video_b200.model.internvl2.modeling_internvl_chat as mod
+    cfg = _chat_cfg()
+
+    class Counting(StubTokenizer):
+        def __init__(self):
+            self.lengths = []
+
+        def __call__(self, text, return_tensors="pt"):
+            self.lengths.append(len(text))
+            return super().__call__(text, return_tensors)
+
+    def full(tok, question, npl):
+        """The reference's statement sequence, with the full text handed to the tokenizer."""
+        from mj_video_b200.model.internvl2.conversation import get_conv_template
+        t = get_conv_template(cfg.template)
+        q = question if "<image>" in question else "<image>\n" + question
+        t.append_message(t.roles[0], q)
+        t.append_message(t.roles[1], None)
+        query = t.get_prompt()
+        for n in npl:
+            query = query.replace("<image>", "<img>" + "<IMG_CONTEXT>" * 256 * n + "</img>", 1)
+        return StubTokenizer()(query)["input_ids"]
+
+    tok = Counting()
+    cases = [("a caption", [8]), ("Frame1: <image>\nFrame2: <image>\nwhat happens?", [1, 3]),
+             ("<image> zero tiles <image>", [0, 2]), ("other caption", [8]), ("third", [2]), ("fourth", [2])]
+    for question, npl in cases:
+        pv = torch.zeros(sum(npl), 3, 448, 448)
+        ids, mask = prepare_chat_input(cfg, tok, pv, question, {}, num_patches_list=npl)
+        assert torch.equal(ids, full(tok, question, npl)) and torch.equal(mask, torch.ones_like(ids))
+    # the first _VERIFY_FIRST calls also tokenised the full text; afterwards only the collapsed prompt (< 1.5 KB) is seen
+    trusted = tok.lengths[2 * mod._VERIFY_FIRST:]
+    assert trusted and max(trusted) < 1500, tok.lengths
+    # a question that itself contains the context token: the count check sends it down the full-text path, same ids
+    q = "why <IMG_CONTEXT> here? <image>"
+    ids, _ = prepare_chat_input(cfg, tok, torch.zeros(1, 3, 448, 448), q, {}, num_patches_list=[1])
+    assert torch.equal(ids, full(tok, q, [1]))
+
+    class Hostile(StubTokenizer):
+        """Appends a marker after every run of two or more context tokens: collapsing the run changes the ids."""
+        def __call__(self, text, return_tensors="pt"):
+            out = super().__call__(text, return_tensors)["input_ids"][0].tolist()
+            res, i = [], 0
+            while i < len(out):
+                j = i
+                while j < len(out) and out[j] == 92546:
+                    j += 1
+                res += out[i:max(j, i + 1)]
+                if j - i >= 2:
+                    res.append(77)
+                i = max(j, i + 1)
+            t = torch.tensor([res], dtype=torch.long)
+            return {"input_ids": t, "attention_mask": torch.ones_like(t)}
+
+    bad = Hostile()
+    for question in ("x", "y", "z"):
+        ids, _ = prepare_chat_input(cfg, bad, torch.zeros(2, 3, 448, 448), question, {}, num_patches_list=[2])
+        t = __import__("mj_video_b200.model.internvl2.conversation", fromlist=["get_conv_template"]).get_conv_template(cfg.template)
+        t.append_message(t.roles[0], "<image>\n" + question)
+        t.append_message(t.roles[1], None)
+        want = bad(t.get_prompt().replace("<image>", "<img>" + "<IMG_CONTEXT>" * 512 + "</img>", 1))["input_ids"]
+        assert torch.equal(ids, want)
+    assert mod._COLLAPSE_STATE[id(bad)][2] is False      # detected on the first call, never collapsed again

@@ -202,3 +202,65 @@ def test_prepare_chat_input_matches_reference_with_history():
         assert len(ref) == len(got) and g1 == g2
         for a, b in zip(ref, got):
             assert torch.equal(a, b) if torch.is_tensor(a) else a == b
+
+
+def test_collate_pairs_matches_reference_video_data_collator():
+    """`pipeline.collate_pairs` against the unmodified `VideoDataCollator` (dataset.py:407-554) on ragged
+    rows. The reference pads every row to max_length (3072) and stacks [B, F, 3, 448, 448] per video side, which its train
+    loop flattens to [B*F, 3, 448, 448] (overall_train.py:70-72); the pair scorer interleaves the two sides row by row
+    (chosen, rejected, chosen, ...) and pads to the batch maximum. Same tokens, same masks, same frame order; the only
+    difference is the amount of trailing padding, which the engine removes anyway (rows are packed)."""
+    import numpy as np
+    from mj_video_b200.pipeline import collate_pairs
+    from oracle import reference_harness as rh
+    ds_mod = rh.reference_dataset_module()
+
+    class Tok:
+        pad_token_id = 2
+
+    rng = np.random.default_rng(5)
+    n_pairs, F = 5, 2
+    rows = {}
+    for k in range(n_pairs):
+        for side in (0, 1):
+            n = int(rng.integers(30, 400))
+            ids = rng.integers(1000, 90000, size=n)
+            frames = rng.integers(0, 256, size=(F, 6 + k, 8, 3), dtype=np.uint8)   # per-pair geometry
+            rows[(k, side)] = (frames, ids.tolist())
+
+    class Pairs:
+        def __len__(self):
+            return n_pairs
+
+        def __getitem__(self, k):
+            return rows[(k, 0)], rows[(k, 1)]
+
+    hb = collate_pairs(Pairs(), list(range(n_pairs)), pad_token_id=2, pin=False)
+
+    def side_dict(k, s):
+        frames, ids = rows[(k, s)]
+        t = torch.tensor(ids, dtype=torch.long)[None]
+        # the reference stacks pixel_values; a [F,3,h,w] float view of the same frames stands in for load_video's output
+        pv = torch.from_numpy(frames).permute(0, 3, 1, 2).float()
+        return dict(input_ids=t, attention_mask=torch.ones_like(t), pixel_values=pv, criteria_score=[0.0], criteria_related=[0],
+                    aspect_score=[0.0], aspect_related=[0], total_score=[0.0], total_related=[0])
+
+    for max_length in (3072, None):
+        coll = ds_mod.VideoDataCollator(Tok(), max_length=max_length)
+        for k in range(n_pairs):     # per pair (the per-pair geometry cannot be stacked across pairs by the reference)
+            ref = coll([dict(video_0_dict=side_dict(k, 0), video_1_dict=side_dict(k, 1),
+                             preference_dict=dict(aspect_preference=[0], aspect_mask=[0], overall_preference=[0],
+                                                  overall_mask=[0]))])
+            for s in (0, 1):
+                r = 2 * k + s
+                rid, rmask = ref[f"video_{s}_input_ids"][0], ref[f"video_{s}_attention_mask"][0]
+                n = int(rmask.sum())
+                assert n == len(rows[(k, s)][1])
+                # identical tokens and mask on the real part, pad id / zero mask on every padded position of both
+                assert torch.equal(hb.input_ids[r, :n], rid[:n]) and torch.equal(hb.attention_mask[r, :n], rmask[:n])
+                assert bool((rid[n:] == 2).all()) and bool((rmask[n:] == 0).all())
+                assert bool((hb.input_ids[r, n:] == 2).all()) and bool((hb.attention_mask[r, n:] == 0).all())
+                # frames of the row, in the order the reference's flattened [B*F, 3, H, W] stack has them
+                flat = ref[f"video_{s}_pixel_values"].view(-1, 3, 6 + k, 8)
+                assert torch.equal(hb.frames[r].permute(0, 3, 1, 2).float(), flat)
+    assert hb.input_ids.shape[1] == max(len(v[1]) for v in rows.values()) and hb.pair_ids == list(range(n_pairs))

@@ -160,6 +160,47 @@ def open_video(video):
         raise RuntimeError("no video decoder available (decord / av / cv2 not installed); pass an array or .npy") from e
 
 
+def sample_clip(video, bound=None, num_segments=32) -> np.ndarray:
+    """The host half of load_video (data.py:164-172): open, `get_index`, decode ONLY the sampled frames -> uint8 [n,H,W,3]."""
+    vr = open_video(video)
+    idx = get_index(bound, float(vr.get_avg_fps()), len(vr) - 1, first_idx=0, num_segments=num_segments)
+    frames = np.ascontiguousarray(vr.take(idx))
+    if frames.ndim != 4 or frames.shape[-1] != 3:
+        raise ValueError(f"expected RGB frames [n,H,W,3], got {frames.shape}")
+    return frames
+
+
+class ClipDecodePool:
+    """Host decode of many clips in parallel (the part that does not need NVDEC). The reference decodes
+    one video at a time on one thread (`VideoReader(..., num_threads=1)`, data.py:164) - about 30 clips/s at best, while one
+    B200 consumes 85 clips/s and a box of eight ~650. decord, PyAV and OpenCV all release the GIL while decoding, so a
+    thread pool scales with the host cores; results come back in submission order and are bit-identical to
+    `sample_clip` called serially (same readers, same `get_index`)."""
+
+    def __init__(self, workers: int = 8, num_segments: int = 8, bound=None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.num_segments, self.bound = num_segments, bound
+        self._ex = ThreadPoolExecutor(max_workers=max(1, int(workers)), thread_name_prefix="mjv-decode")
+
+    def submit(self, video):
+        return self._ex.submit(sample_clip, video, self.bound, self.num_segments)
+
+    def map(self, videos):
+        """Decode `videos` concurrently; yields uint8 clips in input order (a failed clip raises when it is reached)."""
+        futs = [self.submit(v) for v in videos]
+        for f in futs:
+            yield f.result()
+
+    def close(self):
+        self._ex.shutdown(wait=True, cancel_futures=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def preprocess_frames(frames_u8: torch.Tensor, input_size=448, max_num=1, use_thumbnail=True,
                       dtype=torch.float32, out: torch.Tensor | None = None) -> tuple[torch.Tensor, int]:
     """uint8 CUDA tensor [F,H,W,3] -> normalised tiles [F*tiles_per_frame,3,S,S] on the same device.
@@ -193,13 +234,8 @@ def preprocess_frames(frames_u8: torch.Tensor, input_size=448, max_num=1, use_th
 def load_video(video_path, bound=None, input_size=448, max_num=1, num_segments=32, *, device=None, dtype=None):
     """Reference signature (data.py:158). Returns (pixel_values, num_patches_list).
     device=None -> CPU fp32 result like the reference; device='cuda' keeps the tiles on the GPU (optionally bf16)."""
-    vr = open_video(video_path)
-    max_frame = len(vr) - 1
-    fps = float(vr.get_avg_fps())
-    frame_indices = get_index(bound, fps, max_frame, first_idx=0, num_segments=num_segments)
-    frames = np.ascontiguousarray(vr.take(frame_indices))
-    if frames.ndim != 4 or frames.shape[-1] != 3:
-        raise ValueError(f"expected RGB frames [n,H,W,3], got {frames.shape}")
+    frames = sample_clip(video_path, bound, num_segments)
+    frame_indices = range(frames.shape[0])
     if not torch.cuda.is_available():
         raise RuntimeError("load_video (mj_video_b200) preprocesses frames on the GPU; no CUDA device is available")
     gpu = torch.device(device if device is not None else "cuda")

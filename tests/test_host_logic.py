@@ -447,3 +447,28 @@ def test_prepare_chat_input_collapsed_context_runs_are_token_identical():
         want = bad(t.get_prompt().replace("<image>", "<img>" + "<IMG_CONTEXT>" * 512 + "</img>", 1))["input_ids"]
         assert torch.equal(ids, want)
     assert mod._COLLAPSE_STATE[id(bad)][2] is False      # detected on the first call, never collapsed again
+
+
+def test_clip_decode_pool_matches_serial_decode(tmp_path):
+    """SURVEY §8(f) N1 (host part): clips decoded by the thread pool are bit-identical to serial `sample_clip` and come
+    back in submission order."""
+    cv2 = pytest.importorskip("cv2")
+    from mj_video_b200.data_processor import ClipDecodePool, sample_clip
+    paths = []
+    for v in range(5):
+        path = str(tmp_path / f"clip{v}.avi")
+        wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 8.0, (96, 64))
+        vid = synth.make_video(300 + v, n_frames=10 + v, height=64, width=96)
+        for f in vid:
+            wr.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+        wr.release()
+        paths.append(path)
+    serial = [sample_clip(p, None, 4) for p in paths]
+    with ClipDecodePool(workers=3, num_segments=4) as pool:
+        par = list(pool.map(paths))
+        arr = list(pool.map([synth.make_video(7, n_frames=9, height=32, width=48)]))   # in-memory arrays work as well
+    assert len(par) == 5 and all(np.array_equal(a, b) for a, b in zip(serial, par))
+    assert all(c.shape == (4, 64, 96, 3) and c.dtype == np.uint8 for c in par)
+    assert arr[0].shape == (4, 32, 48, 3)
+    with ClipDecodePool(workers=2, num_segments=4) as pool, pytest.raises(Exception):
+        list(pool.map([paths[0], str(tmp_path / "missing.avi")]))

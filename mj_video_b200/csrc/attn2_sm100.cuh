@@ -162,7 +162,31 @@ __device__ __forceinline__ void max_chunk(const uint32_t* v, float* mx) {
 // MUFU.EX2. ptxas otherwise consumes each pair right after the next pair's MUFUs are issued (16 cycles later), which is
 // shorter than the MUFU latency: a warp alone on its scheduler then stalls 8 cycles per pair (24 instead of 16 cycles).
 constexpr int kExpDepth = 3;
-template <int C>
+
+// 2^x for a packed pair WITHOUT the MUFU (the FlashAttention-4 trick): MUFU.EX2 issues one warp instruction per 8 cycles
+// per scheduler, and at head_dim 64 the exponentials, not the tensor cores, bound the kernel; the FMA pipe has slack.
+// Cody-Waite: n = round(x) through the 1.5*2^23 magic add (n lands in the low mantissa bits), f = x - n in [-0.5, 0.5],
+// 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below the bf16 rounding of P), then n is added
+// to the exponent field. Inputs are clamped at -125 (2^-125 ~ 0); masked scores (-inf) never take this path.
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
+    float x0, x1;
+    ptx::unpack_f32x2(x2, x0, x1);
+    const uint64_t xc = ptx::pack_f32x2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    const uint64_t t = ptx::fadd2(xc, ptx::pack_f32x2(12582912.0f, 12582912.0f));
+    const uint64_t n = ptx::fadd2(t, ptx::pack_f32x2(-12582912.0f, -12582912.0f));
+    const uint64_t f = ptx::ffma2(n, ptx::pack_f32x2(-1.0f, -1.0f), xc);
+    uint64_t p = ptx::ffma2(f, ptx::pack_f32x2(0.05517132f, 0.05517132f), ptx::pack_f32x2(0.24261054f, 0.24261054f));
+    p = ptx::ffma2(p, f, ptx::pack_f32x2(0.69326099f, 0.69326099f));
+    p = ptx::ffma2(p, f, ptx::pack_f32x2(0.99992811f, 0.99992811f));
+    float pa, pb, ta, tb;
+    ptx::unpack_f32x2(p, pa, pb);
+    ptx::unpack_f32x2(t, ta, tb);
+    p0 = __int_as_float(__float_as_int(pa) + (__float_as_int(ta) << 23));
+    p1 = __int_as_float(__float_as_int(pb) + (__float_as_int(tb) << 23));
+}
+
+// POLY of every 8 pairs take the polynomial, the others the MUFU
+template <int C, int POLY = 0>
 __device__ __forceinline__ void exp_chunk(const uint32_t* v, uint32_t* pk, uint64_t sc2, uint64_t nm2, uint64_t* ps2) {
     float p[32];
 #pragma unroll
@@ -170,10 +194,14 @@ __device__ __forceinline__ void exp_chunk(const uint32_t* v, uint32_t* pk, uint6
         if (i < 16) {
             const uint64_t t2 = ptx::ffma2(
                 ptx::pack_f32x2(__uint_as_float(v[C * 32 + 2 * i]), __uint_as_float(v[C * 32 + 2 * i + 1])), sc2, nm2);
-            float t0, t1;
-            ptx::unpack_f32x2(t2, t0, t1);
-            p[2 * i] = ptx::ex2_approx(t0);
-            p[2 * i + 1] = ptx::ex2_approx(t1);
+            if ((i & 7) < POLY) {
+                exp2_poly2(t2, p[2 * i], p[2 * i + 1]);
+            } else {
+                float t0, t1;
+                ptx::unpack_f32x2(t2, t0, t1);
+                p[2 * i] = ptx::ex2_approx(t0);
+                p[2 * i + 1] = ptx::ex2_approx(t1);
+            }
         }
         if (i >= kExpDepth) {
             const int k = i - kExpDepth;
@@ -197,7 +225,8 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int& n, int
 
 // DBG (tools only, selected by the launcher when MJV_ATTN_TRACE is set): every barrier wait carries a watchdog that records
 // which wait wedged (role/barrier code) into the host-pinned trace buffer before trapping.
-template <int HD, bool CAUSAL, bool DBG = false>
+// POLY: of every 8 pairs of exponentials in a fully visible block, POLY are evaluated on the FMA pipe (exp2_poly2).
+template <int HD, bool CAUSAL, bool DBG = false, int POLY = 0>
 __global__ void __launch_bounds__(attn2::kThreads, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnArgs args) {
@@ -416,13 +445,13 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                             // one basic block for the whole row: the tail of a chunk (its last pairs wait for the MUFU
                             // latency, then the store) overlaps the exponentials of the next chunk
                             uint32_t pk1[16], pk2[16], pk3[16];
-                            exp_chunk<0>(v, pk, sc2, nm2, ps2);
+                            exp_chunk<0, POLY>(v, pk, sc2, nm2, ps2);
                             ptx::tmem_st_x16(tmem_S, pk);
-                            exp_chunk<1>(v, pk1, sc2, nm2, ps2);
+                            exp_chunk<1, POLY>(v, pk1, sc2, nm2, ps2);
                             ptx::tmem_st_x16(tmem_S + 16, pk1);
-                            exp_chunk<2>(v, pk2, sc2, nm2, ps2);
+                            exp_chunk<2, POLY>(v, pk2, sc2, nm2, ps2);
                             ptx::tmem_st_x16(tmem_S + 32, pk2);
-                            exp_chunk<3>(v, pk3, sc2, nm2, ps2);
+                            exp_chunk<3, POLY>(v, pk3, sc2, nm2, ps2);
                             ptx::tmem_st_x16(tmem_S + 48, pk3);
                         } else {
                             exp_chunk<0>(v, pk, sc2, nm2, ps2);

@@ -24,11 +24,11 @@ static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
     return 0;
 }
 
-template <int HD, bool CAUSAL, bool DBG = false>
+template <int HD, bool CAUSAL, bool DBG = false, int POLY = 0>
 static int launch_attn2_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& a,
                           dim3 grid, cudaStream_t stream, double work) {
     using L = attn2::Smem<HD>;
-    auto kfn = attention2_kernel<HD, CAUSAL, DBG>;
+    auto kfn = attention2_kernel<HD, CAUSAL, DBG, POLY>;
     static PerDeviceOnce once;  // per instantiation and device
     if (once.first()) {
         MJV_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -43,6 +43,10 @@ static int launch_attn2_t(const CUtensorMap& tq, const CUtensorMap& tk, const CU
 
 // MJV_ATTN_IMPL=1 selects the first-generation kernel (attn_sm100.cuh: one 128-row tile per CTA, 64-column blocks, two
 // CTAs per SM) for A/B measurements; the default is attention2_kernel (attn2_sm100.cuh).
+// default share of polynomial exponentials (of 8 pairs) per shape; 0 until a measurement says otherwise
+constexpr int kPolyVit = 0;
+constexpr int kPolyLlm = 0;
+
 static int attn_impl() {
     const char* e = getenv("MJV_ATTN_IMPL");  // read per call so that one process can time both
     return (e != nullptr && e[0] == '1') ? 1 : 2;
@@ -127,6 +131,19 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
         if (a.trace != nullptr) {  // tools: the debug instantiations exist for the two bench shapes only
             if (hd == 64 && !d.causal) return launch_attn2_t<64, false, true>(tq, tk, tv, a, grid2, stream, work);
             if (hd == 128 && d.causal) return launch_attn2_t<128, true, true>(tq, tk, tv, a, grid2, stream, work);
+        }
+        // exponentials on the FMA pipe: POLY of 8 pairs (tools/attn_bench.py sweeps MJV_ATTN_POLY; defaults below)
+        int poly = (hd == 64 && !d.causal) ? kPolyVit : ((hd == 128 && d.causal) ? kPolyLlm : 0);
+        if (const char* pe = getenv("MJV_ATTN_POLY")) poly = atoi(pe);
+        if (hd == 64 && !d.causal) {
+            if (poly == 2) return launch_attn2_t<64, false, false, 2>(tq, tk, tv, a, grid2, stream, work);
+            if (poly == 3) return launch_attn2_t<64, false, false, 3>(tq, tk, tv, a, grid2, stream, work);
+            if (poly == 4) return launch_attn2_t<64, false, false, 4>(tq, tk, tv, a, grid2, stream, work);
+        }
+        if (hd == 128 && d.causal) {
+            if (poly == 2) return launch_attn2_t<128, true, false, 2>(tq, tk, tv, a, grid2, stream, work);
+            if (poly == 3) return launch_attn2_t<128, true, false, 3>(tq, tk, tv, a, grid2, stream, work);
+            if (poly == 4) return launch_attn2_t<128, true, false, 4>(tq, tk, tv, a, grid2, stream, work);
         }
         if (hd == 64) {
             if (d.causal) return launch_attn2_t<64, true>(tq, tk, tv, a, grid2, stream, work);

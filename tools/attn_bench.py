@@ -20,6 +20,7 @@ from mj_video_b200 import ops  # noqa: E402
 dev = "cuda"
 torch.manual_seed(0)
 OUT = {}
+POLY_SWEEP = tuple(int(x) for x in os.environ.get("MJV_BENCH_POLY", "").split(",") if x)
 
 
 def timeit(fn, iters=10, warm=3):
@@ -76,6 +77,18 @@ def vit_case(T, S=1025, H=16, check_tiles=2):
         res[f"impl{impl}"] = {"ms": ms, "tflops": flops / ms / 1e9, "max_err": err, "nan": nan}
         print(f"[vit T{T}] impl{impl}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  err {err:.2e} nan {nan}", flush=True)
     os.environ.pop("MJV_ATTN_IMPL", None)
+    for poly in POLY_SWEEP:   # share of exponentials evaluated on the FMA pipe (of 8 pairs)
+        os.environ["MJV_ATTN_POLY"] = str(poly)
+        out = torch.full((T * S, Cv), float("nan"), device=dev, dtype=torch.bfloat16)
+        run = lambda: ops.attention(qk, qk, vt, out, head_dim=64, heads=H, kv_heads=H, causal=False, scale=0.125,  # noqa: E731
+                                    q_col0=0, k_col0=Cv, nseq=T, seq_len=S)
+        run()
+        torch.cuda.synchronize()
+        err = max((out[t * S:(t + 1) * S].float() - r).abs().max().item() for t, r in refs)
+        ms = timeit(run)
+        res[f"impl2_poly{poly}"] = {"ms": ms, "tflops": flops / ms / 1e9, "max_err": err}
+        print(f"[vit T{T}] impl2 poly {poly}/8: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  err {err:.2e}", flush=True)
+    os.environ.pop("MJV_ATTN_POLY", None)
     try:
         from flash_attn import flash_attn_varlen_qkvpacked_func
         qkv = torch.cat([qk.view(T * S, 2, H, 64), v.reshape(T * S, 1, H, 64)], 1).contiguous()
@@ -131,6 +144,19 @@ def llm_case(lens, H=16, Hkv=8, hd=128, check=2, pair_blocks=False, tag="llm"):
         res[f"impl{impl}"] = {"ms": ms, "tflops": flops / ms / 1e9, "max_err": err, "nan": nan}
         print(f"[{tag}] impl{impl}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  err {err:.2e} nan {nan}", flush=True)
     os.environ.pop("MJV_ATTN_IMPL", None)
+    for poly in (POLY_SWEEP if (hd == 128 and not pair_blocks) else ()):
+        os.environ["MJV_ATTN_POLY"] = str(poly)
+        work = ops.causal_work_list(lens).to(dev)
+        out = torch.full((tot, H * hd), float("nan"), device=dev, dtype=torch.bfloat16)
+        run = lambda: ops.attention(q.reshape(tot, -1), k.reshape(tot, -1), vt, out, head_dim=hd, heads=H, kv_heads=Hkv,  # noqa: E731
+                                    causal=True, scale=scale, cu_seqlens=cu, work=work, vt_starts=vts, vt_cols=cols)
+        run()
+        torch.cuda.synchronize()
+        err = max((out[a:b].float() - r).abs().max().item() for a, b, r in refs)
+        ms = timeit(run)
+        res[f"impl2_poly{poly}"] = {"ms": ms, "tflops": flops / ms / 1e9, "max_err": err}
+        print(f"[{tag}] impl2 poly {poly}/8: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  err {err:.2e}", flush=True)
+    os.environ.pop("MJV_ATTN_POLY", None)
     try:
         from flash_attn import flash_attn_varlen_func
         mx = max(lens)

@@ -56,27 +56,39 @@ normalize_tiles_kernel(const uint8_t* __restrict__ in, TOut* __restrict__ out, l
     __syncthreads();
     const int groups_per_row = S / 16;
     const long long total = n_tiles * S * groups_per_row;
-    for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
-         g += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int gx = static_cast<int>(g % groups_per_row);
-        const long long ty = g / groups_per_row;
-        const int y = static_cast<int>(ty % S);
-        const long long t = ty / S;
-        const uint4* src = reinterpret_cast<const uint4*>(in + ((t * S + y) * S + gx * 16) * 3);
-        uint4 raw[3];
-        raw[0] = __ldg(src);
-        raw[1] = __ldg(src + 1);
-        raw[2] = __ldg(src + 2);
-        const uint8_t* b = reinterpret_cast<const uint8_t*>(raw);
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    constexpr int U = 4;  // groups per thread and trip: 12 independent 16-byte loads in flight before the first use
+    for (long long g0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g0 < total; g0 += U * stride) {
+        uint4 raw[U][3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            __align__(16) TOut vals[16];
+        for (int k = 0; k < U; ++k) {
+            const long long g = g0 + k * stride;
+            if (g < total) {
+                const uint4* src = reinterpret_cast<const uint4*>(in + g * 48);   // 16 pixels x 3 bytes, row-major HWC
+                raw[k][0] = __ldg(src);
+                raw[k][1] = __ldg(src + 1);
+                raw[k][2] = __ldg(src + 2);
+            }
+        }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) vals[i] = cvt_out<TOut>(lut[c * 256 + b[i * 3 + c]]);
-            TOut* dst = out + ((t * 3 + c) * S + y) * S + gx * 16;
-            const uint4* v4 = reinterpret_cast<const uint4*>(vals);
+        for (int k = 0; k < U; ++k) {
+            const long long g = g0 + k * stride;
+            if (g >= total) break;
+            const int gx = static_cast<int>(g % groups_per_row);
+            const long long ty = g / groups_per_row;
+            const int y = static_cast<int>(ty % S);
+            const long long t = ty / S;
+            const uint8_t* b = reinterpret_cast<const uint8_t*>(raw[k]);
 #pragma unroll
-            for (int i = 0; i < static_cast<int>(sizeof(TOut) * 16 / 16); ++i) reinterpret_cast<uint4*>(dst)[i] = v4[i];
+            for (int c = 0; c < 3; ++c) {
+                __align__(16) TOut vals[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) vals[i] = cvt_out<TOut>(lut[c * 256 + b[i * 3 + c]]);
+                TOut* dst = out + ((t * 3 + c) * S + y) * S + gx * 16;
+                const uint4* v4 = reinterpret_cast<const uint4*>(vals);
+#pragma unroll
+                for (int i = 0; i < static_cast<int>(sizeof(TOut) * 16 / 16); ++i) reinterpret_cast<uint4*>(dst)[i] = v4[i];
+            }
         }
     }
 }

@@ -12,7 +12,7 @@ from mj_video_b200 import ops, synth  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--kernel", default=None, choices=[None, "swiglu", "gelu", "resid_fc2", "qkv_vit", "attn_vit", "attn_llm",
-                                                   "layernorm", "rmsnorm"])
+                                                   "layernorm", "rmsnorm", "gather_ln", "frames", "im2col"])
 ap.add_argument("--batch", type=int, default=32)
 args = ap.parse_args()
 dev = "cuda"
@@ -92,6 +92,24 @@ elif args.kernel == "rmsnorm":
     o = torch.empty_like(x)
     lib = _lib.load()
     fn = lambda: lib.mjv_rmsnorm(x.data_ptr(), w.data_ptr(), o.data_ptr(), Ml, 2048, 1e-5, None, _lib.current_stream())  # noqa: E731
+elif args.kernel == "gather_ln":
+    from mj_video_b200 import _lib
+    x, w, b = rnd(Mv, 1024, scale=1.0), rnd(4096), rnd(4096)
+    o = torch.empty(256 * 256, 4096, device=dev, dtype=torch.bfloat16)
+    lib = _lib.load()
+    fn = lambda: lib.mjv_pixel_shuffle_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), o.data_ptr(), 256, 1025, 1024, 1e-5, 0,  # noqa: E731
+                                                 _lib.current_stream())
+elif args.kernel == "frames":
+    from mj_video_b200.data_processor import preprocess_frames
+    fr = torch.randint(0, 256, (256, 448, 448, 3), device=dev, dtype=torch.uint8)
+    px = torch.empty(256, 3, 448, 448, device=dev, dtype=torch.bfloat16)
+    fn = lambda: preprocess_frames(fr, 448, 1, True, torch.bfloat16, out=px)  # noqa: E731
+elif args.kernel == "im2col":
+    from mj_video_b200 import _lib
+    px = rnd(256, 3, 448, 448, scale=1.0)
+    o = torch.empty(256 * 1024, 640, device=dev, dtype=torch.bfloat16)
+    lib = _lib.load()
+    fn = lambda: lib.mjv_im2col_patches(px.data_ptr(), _lib.MJV_DTYPE_BF16, o.data_ptr(), 256, 448, 14, 640, _lib.current_stream())  # noqa: E731
 for _ in range(2):
     fn()
 torch.cuda.synchronize()

@@ -29,6 +29,12 @@
 #pragma once
 #include "attn_sm100.cuh"
 
+#ifndef MJV_TRACE_EPI
+#define MJV_TRACE_EPI 0   // tools: record the epilogue (tags 20-23) instead of the S issuer in trace role 3
+#endif
+#ifndef MJV_ATTN_PSMEM
+#define MJV_ATTN_PSMEM 1
+#endif
 namespace mjv {
 namespace attn2 {
 
@@ -43,18 +49,25 @@ template <int HD>
 struct Smem {
     // score buffers in TMEM: head_dim 64 leaves room for three (3 x 128 + 2 x 64 = 512 columns), so S of a tile's NEXT block
     // is computed while its softmax still works on the current one; head_dim 128 fills TMEM with two (2 x 128 + 2 x 128)
+    static constexpr bool kPSmem = HD == 128 && MJV_ATTN_PSMEM;   // P through shared memory (see below)
     static constexpr int kNSB = HD == 64 ? 3 : 2;
     static constexpr int kQSets = HD == 64 ? 2 : 1;    // item-level double buffering of the Q tile pair
     static constexpr int kQBufs = 2 * kQSets;
-    static constexpr int kKStages = HD == 64 ? 3 : 2;
+    static constexpr int kKStages = HD == 64 ? 3 : (kPSmem ? 1 : 2);
     static constexpr int kVStages = HD == 64 ? 3 : 2;
     static constexpr int kQBytes = BQ * HD * 2;
     static constexpr int kKBytes = BKV * HD * 2;
     static constexpr int kVBytes = HD * BKV * 2;
+    // head_dim 128: TMEM is full (2 x 128 S + 2 x 128 O), so with P written over S the next S of a tile could only be issued
+    // after P·V of the current one (each warpgroup waited ~1400 of its ~3800-cycle step). There P goes through shared memory
+    // instead (one tile per query tile, SS-form P·V) and the score buffer is handed back as soon as the row is in registers.
+    // The 64 KB come from K: one stage instead of two - S is now issued a whole step ahead, which hides the K load.
+    static constexpr int kPBytes = kPSmem ? 2 * BQ * BKV * 2 : 0;   // one P tile per query tile
     static constexpr int kQOff = 0;
     static constexpr int kKOff = kQOff + kQBufs * kQBytes;
     static constexpr int kVOff = kKOff + kKStages * kKBytes;
-    static constexpr int kLOff = kVOff + kVStages * kVBytes;  // row sums handed to the epilogue: [2][128] fp32
+    static constexpr int kPOff = kVOff + kVStages * kVBytes;
+    static constexpr int kLOff = kPOff + kPBytes;                // row sums handed to the epilogue: [2][128] fp32
     static constexpr int kBarOff = kLOff + 2 * BQ * 4;
     static constexpr int kTotal = kBarOff + 512;
 };
@@ -211,6 +224,18 @@ __device__ __forceinline__ void exp_chunk(const uint32_t* v, uint32_t* pk, uint6
     }
 }
 
+// 32 keys of one row (exp_chunk's 16 bf16 pairs = four 16-byte chunks) into the shared P tile (SW128, K-major)
+template <int C>
+__device__ __forceinline__ void st_p_smem(uint32_t prow, uint32_t rx, const uint32_t* pk) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t c = (C & 1) * 4 + q;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (C >> 1) * 16384 + ((c ^ rx) << 4)),
+                     "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                     : "memory");
+    }
+}
+
 // tools only: event k of a role -> trace[role*2*kTraceEvents + 2k] = clock64, [.. + 1] = tag << 32 | step
 __device__ __forceinline__ void trace_ev(long long* trace, int role, int& n, int tag, int step) {
     if (n < kTraceEvents) {
@@ -259,7 +284,12 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     uint64_t* o_done = pv_done + kNSB;       // [2] accumulator of tile t complete (MMA -> epilogue)
     uint64_t* o_empty = o_done + 2;          // [2] accumulator read out (epilogue -> MMA / softmax), 4 warp arrivals
     uint64_t* l_ready = o_empty + 2;         // [2] row sums in smem (softmax -> epilogue), 4 warp arrivals
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_ready + 2);
+    // P-in-smem mode (head_dim 128) only:
+    uint64_t* s_free = l_ready + 2;          // [kNSB] scores of that buffer are in registers (softmax -> S issuer), 4 warp arrivals
+    uint64_t* pvd = s_free + kNSB;           // [2] every P·V of tile t: O_t updated and the tile's P buffer read
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pvd + 2);
+    constexpr bool PSMEM = L::kPSmem;
+    uint8_t* sP = smem + L::kPOff;
 
     // shuffled from lane 0 so that the compiler knows it is warp-uniform (role indices, TMEM addresses -> uniform registers)
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -301,9 +331,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             ptx::mbar_init(&s_full[kNSB + b], 1);
             ptx::mbar_init(&p_full[b], 4);
             ptx::mbar_init(&pv_done[b], 1);
+            ptx::mbar_init(&s_free[b], 4);
         }
         for (int t = 0; t < 2; ++t) {
             ptx::mbar_init(&o_done[t], 1);
+            ptx::mbar_init(&pvd[t], 1);
             ptx::mbar_init(&o_empty[t], 4);
             ptx::mbar_init(&l_ready[t], 4);
         }
@@ -362,6 +394,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     if (++my_slot == kNSB) { my_slot = 0; my_ph ^= 1; }
                     if (tracing) trace_ev(args.trace, tt, n_tr, 1, (int)n_mine);
                     const uint32_t tmem_S = tmem_base + sb * BKV + lane_sel;
+                    // P-in-smem mode, once the scores are in registers (every warp of the tile, rows or not): hand the score
+                    // buffer back to the S issuer and wait for this tile's previous P·V - O_t may then be rescaled, the
+                    // tile's P buffer overwritten, and p_full[tt] (one phase per step of the tile) arrived on again.
+                    auto psmem_handoff = [&]() {
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&s_free[sb]);
+                        if (n_mine > 0) wait_wd(&pvd[tt], (n_mine - 1) & 1, 2);
+                        ptx::tc_fence_after();
+                    };
                     const int kv0 = j * BKV;
                     const int valid = min(BKV, kv_end - kv0);                    // columns of this block that exist
                     const int lim = CAUSAL ? min(valid, qrow - kv0 + 1) : valid;  // per-row visible columns
@@ -402,6 +444,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                             if (nch > 3) max_chunk<3>(v, mx);
                         }
                         const float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2;  // scale > 0
+                        if constexpr (PSMEM) psmem_handoff();
                         // ---- lazy rescale of the TMEM accumulator
                         float alpha = 1.0f;
                         bool need = false;
@@ -416,7 +459,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                             // The previous P·V of this tile must have landed in O_t. pv_done is kept per score buffer so that
                             // the parity wait is exact: that buffer's previous use completed before S of the previous step
                             // was issued, and its next use needs a P that does not exist yet - the count is n-1 or n.
-                            wait_wd(&pv_done[prev_sb], prev_sph, 2);
+                            if constexpr (!PSMEM) wait_wd(&pv_done[prev_sb], prev_sph, 2);
                             ptx::tc_fence_after();
                             l_run *= alpha;
 #pragma unroll 1
@@ -441,7 +484,44 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         uint32_t zero16[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) zero16[i] = 0u;
-                        if (full) {
+                        if constexpr (PSMEM) {
+                            // K-major SW128 tile [128 rows][2 atoms of 64 keys]: 16-byte chunk c of row r sits at c ^ (r & 7)
+                            const uint32_t prow = ptx::smem_u32(sP) + tt * (BQ * BKV * 2) + (r >> 3) * 1024 + (r & 7) * 128;
+                            const uint32_t rx = r & 7;
+                            if (full) {
+                                uint32_t pk1[16], pk2[16], pk3[16];
+                                exp_chunk<0, POLY>(v, pk, sc2, nm2, ps2);
+                                st_p_smem<0>(prow, rx, pk);
+                                exp_chunk<1, POLY>(v, pk1, sc2, nm2, ps2);
+                                st_p_smem<1>(prow, rx, pk1);
+                                exp_chunk<2, POLY>(v, pk2, sc2, nm2, ps2);
+                                st_p_smem<2>(prow, rx, pk2);
+                                exp_chunk<3, POLY>(v, pk3, sc2, nm2, ps2);
+                                st_p_smem<3>(prow, rx, pk3);
+                            } else {
+                                exp_chunk<0>(v, pk, sc2, nm2, ps2);
+                                st_p_smem<0>(prow, rx, pk);
+                                if (nch > 1) {
+                                    exp_chunk<1>(v, pk, sc2, nm2, ps2);
+                                    st_p_smem<1>(prow, rx, pk);
+                                } else if (pch > 1) {
+                                    st_p_smem<1>(prow, rx, zero16);
+                                }
+                                if (nch > 2) {
+                                    exp_chunk<2>(v, pk, sc2, nm2, ps2);
+                                    st_p_smem<2>(prow, rx, pk);
+                                } else if (pch > 2) {
+                                    st_p_smem<2>(prow, rx, zero16);
+                                }
+                                if (nch > 3) {
+                                    exp_chunk<3>(v, pk, sc2, nm2, ps2);
+                                    st_p_smem<3>(prow, rx, pk);
+                                } else if (pch > 3) {
+                                    st_p_smem<3>(prow, rx, zero16);
+                                }
+                            }
+                            ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+                        } else if (full) {
                             // one basic block for the whole row: the tail of a chunk (its last pairs wait for the MUFU
                             // latency, then the store) overlaps the exponentials of the next chunk
                             uint32_t pk1[16], pk2[16], pk3[16];
@@ -480,14 +560,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         ptx::unpack_f32x2(ptx::fadd2(ps2[2], ps2[3]), s2, s3);
                         l_run += (s0 + s1) + (s2 + s3);
                         if (tracing) trace_ev(args.trace, tt, n_tr, 3, (int)n_mine);
-                        ptx::tmem_wait_st();
+                        if constexpr (!PSMEM) ptx::tmem_wait_st();
                         if (tracing) trace_ev(args.trace, tt, n_tr, 4, (int)n_mine);
+                    } else {
+                        if constexpr (PSMEM) psmem_handoff();
                     }
                     ptx::tc_fence_before();
                     __syncwarp();
                     // A warp without rows still waits for s_full above: S of the step that reuses this buffer (and this p_full
                     // barrier) is only issued after the P·V of this step, i.e. after all four arrivals of this phase.
-                    if (lane == 0) ptx::mbar_arrive(&p_full[sb]);
+                    if (lane == 0) ptx::mbar_arrive(&p_full[PSMEM ? tt : sb]);
                     ++n_mine;
                     prev_sb = sb;
                     prev_sph = sph;
@@ -513,19 +595,28 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int r = qw * 32 + lane;
         const uint32_t lane_sel = static_cast<uint32_t>(qw * 32) << 16;
         uint32_t n_use[2] = {0, 0};
+        [[maybe_unused]] const bool tracing = MJV_TRACE_EPI && args.trace != nullptr && blockIdx.x == 0 && warp == 8 && lane == 0;
+        [[maybe_unused]] int n_tr = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const Item t = decode_item<CAUSAL>(args, it);
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
                 if (t.nblk[tt] == 0) continue;
                 if constexpr (DBG) dbg_aux = (static_cast<long long>(it) << 32) | (tt << 16) | n_use[tt];
+                if (MJV_TRACE_EPI && tracing) trace_ev(args.trace, 3, n_tr, 20, (int)(n_use[tt] * 2 + tt));
                 wait_wd(&l_ready[tt], n_use[tt] & 1, 4);
+                if (MJV_TRACE_EPI && tracing) trace_ev(args.trace, 3, n_tr, 21, (int)(n_use[tt] * 2 + tt));
                 wait_wd(&o_done[tt], n_use[tt] & 1, 5);
+                if (MJV_TRACE_EPI && tracing) trace_ev(args.trace, 3, n_tr, 22, (int)(n_use[tt] * 2 + tt));
                 ptx::tc_fence_after();
                 const int qrow = t.q0[tt] + r;
                 const bool warp_has_rows = (t.q0[tt] + qw * 32) < t.len;
                 if (warp_has_rows) {
                     const float inv = 1.0f / sL[tt * BQ + r];
+                    // One thread owns one row in TMEM: a store instruction writes 16 bytes of 32 different rows. A variant that
+                    // transposed 4 x 4 quads inside lane groups (8 rows x 64 contiguous bytes per instruction) measured no
+                    // faster: the drain (2500-4500 cycles per tile, tools/attn_trace.py with -DMJV_TRACE_EPI=1) is bound by
+                    // the issue slots this warpgroup gets beside the two softmax warpgroups, not by the LSU.
                     __nv_bfloat16* dst =
                         args.out + static_cast<long long>(t.row_base + qrow) * args.ldo + t.h[tt] * args.out_hd;
                     const uint32_t tmem_O = tmem_O0 + tt * HD + lane_sel;
@@ -548,6 +639,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         }
                     }
                 }
+                if (MJV_TRACE_EPI && tracing) trace_ev(args.trace, 3, n_tr, 23, (int)(n_use[tt] * 2 + tt));
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&o_empty[tt]);
@@ -587,6 +679,17 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                              args.k_col0 + t.kvh * HD + kd * 64, t.tma_row0 + j * BKV, t.tma_batch,
                                              ptx::kEvictLast);
                         if (++kst == KS) { kst = 0; kph ^= 1; }
+                        if constexpr (KS == 1) {
+                            // single K stage: the next block's load can only be issued when S of this one has retired - pull
+                            // it into L2 now, so that load costs an L2 hit (~700 cycles) and not an HBM round trip (~2200,
+                            // tools/attn_trace.py: score waits of 1250 cycles per step whenever K came from HBM)
+                            if (j + 1 < t.nblk_max) {
+#pragma unroll
+                                for (int kd = 0; kd < HD / 64; ++kd)
+                                    ptx::tma_prefetch_3d(&tmK, args.k_col0 + t.kvh * HD + kd * 64, t.tma_row0 + (j + 1) * BKV,
+                                                         t.tma_batch);
+                            }
+                        }
                         wait_sp(&v_empty[vst], vph ^ 1, 12);
                         ptx::mbar_expect_tx(&v_full[vst], L::kVBytes);
 #pragma unroll
@@ -608,12 +711,14 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const bool leader = ptx::elect_one();
             constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD);
             const uint64_t v_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sV));
+            [[maybe_unused]] const uint64_t p_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sP));
             int vst = 0;
             uint32_t vph = 0;
             int g = 0;
             int p_sb = 0;             // score buffer holding P of the next P·V step
             uint32_t p_ph = 0;
             uint32_t o_use[2] = {0, 0};
+            [[maybe_unused]] uint32_t p_use[2] = {0, 0};   // P-in-smem mode: steps of each tile so far (p_full[tt] phases)
             const bool tracing = args.trace != nullptr && blockIdx.x == 0 && leader;
             int n_tr = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -636,7 +741,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         const int ksteps = (valid + 15) >> 4;
                         const uint32_t p_tmem = tmem_base + p_sb * BKV;  // P_g: bf16 pairs in the first 64 columns
                         const uint32_t o_tmem = tmem_O0 + tt * HD;
-                        wait_sp(&p_full[p_sb], p_ph, 22);
+                        if constexpr (PSMEM) wait_sp(&p_full[tt], sel2(tt, p_use) & 1, 22);
+                        else wait_sp(&p_full[p_sb], p_ph, 22);
                         ptx::tc_fence_after();
                         if (tracing) trace_ev(args.trace, 2, n_tr, 10, g);
                         if (leader) {
@@ -644,10 +750,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                             for (int ks = 0; ks < BKV / 16; ++ks) {
                                 if (ks < ksteps) {
                                     const uint64_t b = vb0 + static_cast<uint64_t>(((ks >> 2) * (HD * 128) + (ks & 3) * 32) >> 4);
-                                    ptx::mma_bf16_ts(o_tmem, p_tmem + ks * 8, b, idesc_o, (j | ks) != 0 ? 1u : 0u);
+                                    if constexpr (PSMEM) {
+                                        const uint64_t a = p_desc0 + static_cast<uint64_t>((tt * (BQ * BKV * 2) + (ks >> 2) * (BQ * 128) + (ks & 3) * 32) >> 4);
+                                        ptx::mma_bf16_ss(o_tmem, a, b, idesc_o, (j | ks) != 0 ? 1u : 0u);
+                                    } else {
+                                        ptx::mma_bf16_ts(o_tmem, p_tmem + ks * 8, b, idesc_o, (j | ks) != 0 ? 1u : 0u);
+                                    }
                                 }
                             }
-                            ptx::mma_commit(&pv_done[p_sb]);
+                            if constexpr (PSMEM) ptx::mma_commit(&pvd[tt]);
+                            else ptx::mma_commit(&pv_done[p_sb]);
                             if (last_of_tile) ptx::mma_commit(&o_done[tt]);
                             if (last_of_block) ptx::mma_commit(&v_empty[vst]);
                         }
@@ -661,6 +773,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                             if (++vst == VS) { vst = 0; vph ^= 1; }
                         }
                         ++g;
+                        if constexpr (PSMEM) {
+                            if (tt != 0) ++p_use[1];
+                            else ++p_use[0];
+                        }
                         if (++p_sb == kNSB) { p_sb = 0; p_ph ^= 1; }
                     }
                 }
@@ -678,7 +794,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             int sb = 0;               // score buffer of the next S step
             uint32_t sph = 0;         // parity of its CURRENT use; its previous use completed pv_done[sb] in phase sph ^ 1
             bool wrapped = false;     // every buffer has been used once
-            const bool tracing = args.trace != nullptr && blockIdx.x == 0 && leader;
+            const bool tracing = !MJV_TRACE_EPI && args.trace != nullptr && blockIdx.x == 0 && leader;
             int n_tr = 0;
             int gs = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -697,7 +813,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         if (j == 0) wait_sp(&q_full[buf], (use / QSETS) & 1, 30);
                         if (first_of_block) wait_sp(&k_full[kst], kph, 31);
                         // the P·V that read this buffer's previous contents (P of step gs - kNSB) has completed
-                        if (wrapped) wait_sp(&pv_done[sb], sph ^ 1, 32);
+                        // (P-in-smem mode: its scores have been read into registers - P·V no longer touches the buffer)
+                        if (wrapped) wait_sp(PSMEM ? &s_free[sb] : &pv_done[sb], sph ^ 1, 32);
                         ptx::tc_fence_after();
                         const uint64_t a0 = q_desc0 + static_cast<uint64_t>((buf * L::kQBytes) >> 4);
                         const uint32_t d = tmem_base + sb * BKV;

@@ -159,6 +159,12 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         "r"(c2), "l"(hint)
         : "memory");
 }
+// TMA prefetch of a tile into L2 (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 
 // TMA store: shared -> global tile (bulk async group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {

@@ -211,6 +211,8 @@ if __name__ == "__main__":
         g = torch.Generator().manual_seed(1)
         lens = (2141 + torch.randint(16, 97, (32,), generator=g)).tolist()
         OUT["llm"] = llm_case(lens, tag="llm")
+    if "llmlong" in what:  # BASELINE configs[3] shaped rows (16 frames x 7 tiles): items of up to 225 key blocks
+        OUT["llmlong"] = llm_case([28800, 28800, 300], check=0, tag="llmlong")
     if "mha" in what:
         OUT["mha"] = llm_case([2187] * 16, H=32, Hkv=32, hd=128, pair_blocks=True, tag="mha")
     if "gemm" in what:

@@ -68,7 +68,12 @@ struct Smem {
     static constexpr int kVOff = kKOff + kKStages * kKBytes;
     static constexpr int kPOff = kVOff + kVStages * kVBytes;
     static constexpr int kLOff = kPOff + kPBytes;                // row sums handed to the epilogue: [2][128] fp32
-    static constexpr int kBarOff = kLOff + 2 * BQ * 4;
+    // trailing-key path (head_dim 64 only): p of the last key per row [2][128] fp32, its V row per tile [2][64] fp32, and
+    // the key's scaled score per row [2][128] (parked in shared memory between the first step and the end of the item:
+    // one more live register in the softmax loop cost 370 cycles per step)
+    static constexpr int kTailOff = kLOff + 2 * BQ * 4;
+    static constexpr int kTailBytes = HD == 64 ? 2 * BQ * 4 + 2 * HD * 4 + 2 * BQ * 4 : 0;   // + the key's score per row
+    static constexpr int kBarOff = kTailOff + kTailBytes;
     static constexpr int kTotal = kBarOff + 512;
 };
 
@@ -76,6 +81,7 @@ struct Smem {
 // sel2() picks by a runtime tile number
 struct Item {
     int row_base, len, tma_row0, tma_batch, kvh, v_plane, v_col0, nblk_max;
+    int dual;   // the two tiles read different K/V (heads h, h+1): every step has its own K and V stage
     int h[2], q0[2], kv_end[2], nblk[2];
 };
 __device__ __forceinline__ int sel2(int t, const int* a) { return t != 0 ? a[1] : a[0]; }
@@ -84,6 +90,7 @@ __device__ __forceinline__ uint32_t sel2(int t, const uint32_t* a) { return t !=
 template <bool CAUSAL>
 __device__ __forceinline__ Item decode_item(const AttnArgs& a, int it) {
     Item t;
+    t.dual = 0;
     int seq, qb0, qb1;
     bool has1;
     if (a.work != nullptr) {
@@ -105,6 +112,24 @@ __device__ __forceinline__ Item decode_item(const AttnArgs& a, int it) {
             qb1 = hi - 1;
             t.h[0] = t.h[1] = it % a.heads;
         }
+    } else if (a.pair_tail) {
+        // per sequence: heads x (n_qblocks / 2) two-block items, then heads / 2 items pairing the odd last q-block of two heads
+        const int np = a.n_qblocks >> 1;
+        const int full = a.heads * np;
+        const int per_seq = full + (a.heads >> 1);
+        seq = it / per_seq;
+        const int r = it - seq * per_seq;
+        if (r < full) {
+            t.h[0] = t.h[1] = r / np;
+            qb0 = 2 * (r % np);
+            qb1 = qb0 + 1;
+        } else {
+            t.h[0] = 2 * (r - full);
+            t.h[1] = t.h[0] + 1;
+            qb0 = qb1 = a.n_qblocks - 1;
+            t.dual = 1;
+        }
+        has1 = true;
     } else {
         const int npairs = (a.n_qblocks + 1) >> 1;
         const int pr = it % npairs;
@@ -124,8 +149,8 @@ __device__ __forceinline__ Item decode_item(const AttnArgs& a, int it) {
     }
     t.q0[0] = qb0 * BQ;
     t.q0[1] = qb1 * BQ;
-    t.kv_end[0] = CAUSAL ? min(t.len, t.q0[0] + BQ) : t.len;
-    t.kv_end[1] = CAUSAL ? min(t.len, t.q0[1] + BQ) : t.len;
+    t.kv_end[0] = CAUSAL ? min(t.len, t.q0[0] + BQ) : t.len - a.kv_tail;
+    t.kv_end[1] = CAUSAL ? min(t.len, t.q0[1] + BQ) : t.len - a.kv_tail;
     t.nblk[0] = (t.kv_end[0] + BKV - 1) / BKV;
     t.nblk[1] = has1 ? (t.kv_end[1] + BKV - 1) / BKV : 0;
     t.nblk_max = max(t.nblk[0], t.nblk[1]);
@@ -139,7 +164,7 @@ __device__ __forceinline__ Item decode_item(const AttnArgs& a, int it) {
 
 // what the MMA issuer needs of an item (it tracks two items at once: the S stream runs ahead of the P·V stream)
 struct ItemLite {
-    int nblk[2], kv_end[2], nblk_max;
+    int nblk[2], kv_end[2], nblk_max, dual;
 };
 template <bool CAUSAL>
 __device__ __forceinline__ ItemLite decode_lite(const AttnArgs& a, int it) {
@@ -150,6 +175,7 @@ __device__ __forceinline__ ItemLite decode_lite(const AttnArgs& a, int it) {
     l.kv_end[0] = t.kv_end[0];
     l.kv_end[1] = t.kv_end[1];
     l.nblk_max = t.nblk_max;
+    l.dual = t.dual;
     return l;
 }
 
@@ -266,6 +292,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     uint8_t* sK = smem + L::kKOff;
     uint8_t* sV = smem + L::kVOff;
     float* sL = reinterpret_cast<float*>(smem + L::kLOff);
+    constexpr bool KVT = !CAUSAL && HD == 64;   // the trailing-key path exists in this instantiation (args.kv_tail turns it on)
+    [[maybe_unused]] float* sPT = reinterpret_cast<float*>(smem + L::kTailOff);        // [2][BQ]
+    [[maybe_unused]] float* sVT = reinterpret_cast<float*>(smem + L::kTailOff) + 2 * BQ;  // [2][HD]
+    [[maybe_unused]] float* sMT = reinterpret_cast<float*>(smem + L::kTailOff) + 2 * BQ + 2 * HD;  // [2][BQ]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
     uint64_t* q_full = bars;                 // [4]
     uint64_t* q_empty = bars + 4;            // [4]  Q tile consumed by the last S MMA of its item
@@ -354,7 +384,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int wg = warp >> 2;
     if (wg < 2) {
         // ===================================================== softmax of query tile `wg` (TMEM lane == query row)
-        ptx::setmaxnreg_inc<184>();
+        ptx::setmaxnreg_inc<192>();
         const int tt = wg;
         const int qw = warp & 3;
         const int r = qw * 32 + lane;
@@ -369,7 +399,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         uint32_t prev_sph = 0;
         uint32_t n_use = 0;   // items in which this tile was active so far
         const float scale_log2 = args.scale_log2;
-        const bool tracing = args.trace != nullptr && blockIdx.x == 0 && qw == 0 && lane == 0;
+        const bool tracing = DBG && args.trace != nullptr && blockIdx.x == 0 && qw == 0 && lane == 0;
         int n_tr = 0;
 
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -381,6 +411,40 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const bool warp_has_rows = (q0 + qw * 32) < len;  // warp-uniform
             float m_run = -INFINITY;
             float l_run = 0.0f;
+            if constexpr (KVT) {
+                float m_tail = -INFINITY;   // score of the trailing key, scaled to the log2 domain
+                if (args.kv_tail != 0 && my_nblk > 0) {
+                    // s_last = q_row . k_last on the CUDA cores: the row from the swizzled Q tile (TMA has landed: q_full), the
+                    // key row straight from global (one address per warp). Products of bf16 pairs are exact in fp32, as on
+                    // the tensor core. The tile cannot be reloaded before this read: an item has more key blocks than there
+                    // are score buffers, so its last S needs a P of this item first.
+                    const int buf = (n_use % QSETS) * 2 + tt;
+                    wait_wd(&q_full[buf], (n_use / QSETS) & 1, 7);
+                    if (warp_has_rows) {
+                        const uint32_t qaddr = ptx::smem_u32(sQ) + buf * L::kQBytes + (r >> 3) * 1024 + (r & 7) * 128;
+                        const uint4* kt = reinterpret_cast<const uint4*>(
+                            args.k_ptr + static_cast<long long>(t.row_base + len - 1) * args.ldk + args.k_col0 +
+                            (t.kvh + (t.dual ? tt : 0)) * HD);
+                        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            uint32_t q4[4];
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(q4[0]), "=r"(q4[1]), "=r"(q4[2]), "=r"(q4[3])
+                                         : "r"(qaddr + ((c ^ (r & 7)) << 4)));
+                            const uint4 k4 = __ldg(kt + c);
+                            const uint32_t kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                acc0 = fmaf(__uint_as_float(q4[i] << 16), __uint_as_float(kk[i] << 16), acc0);
+                                acc1 = fmaf(__uint_as_float(q4[i] & 0xffff0000u), __uint_as_float(kk[i] & 0xffff0000u), acc1);
+                            }
+                        }
+                        m_tail = (acc0 + acc1) * scale_log2;
+                    }
+                }
+                sMT[tt * BQ + r] = m_tail;   // private to this thread: no synchronisation
+            }
 
             for (int j = 0; j < t.nblk_max; ++j) {
                 if constexpr (DBG) dbg_aux = (static_cast<long long>(it) << 32) | (static_cast<long long>(j) << 16) | (sb << 8) | sph;
@@ -450,6 +514,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         bool need = false;
                         if (j == 0) {
                             m_run = bm;
+                            if constexpr (KVT) {   // the trailing key is the first "block" of the online softmax (p = 2^(m_tail - m))
+                                const float m_tail = sMT[tt * BQ + r];
+                                m_run = fmaxf(bm, m_tail);
+                                l_run = ptx::ex2_approx(m_tail - m_run);
+                            }
                         } else if (bm > m_run + kRescaleThreshold) {
                             alpha = ptx::ex2_approx(m_run - bm);
                             m_run = bm;
@@ -583,6 +652,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 // hand the row sums to the epilogue warpgroup (which must be done with the previous item's)
                 if (n_use > 0) wait_wd(&o_empty[tt], (n_use - 1) & 1, 3);
                 sL[tt * BQ + r] = l_run;
+                if constexpr (KVT) sPT[tt * BQ + r] = ptx::ex2_approx(sMT[tt * BQ + r] - m_run);   // 0 when the path is off (-inf)
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&l_ready[tt]);
                 ++n_use;
@@ -590,15 +660,28 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
     } else if (wg == 2) {
         // ===================================================== epilogue: O_t / l -> bf16 -> global
-        ptx::setmaxnreg_dec<80>();
+        ptx::setmaxnreg_dec<72>();
         const int qw = warp & 3;
         const int r = qw * 32 + lane;
         const uint32_t lane_sel = static_cast<uint32_t>(qw * 32) << 16;
         uint32_t n_use[2] = {0, 0};
-        [[maybe_unused]] const bool tracing = MJV_TRACE_EPI && args.trace != nullptr && blockIdx.x == 0 && warp == 8 && lane == 0;
+        [[maybe_unused]] const bool tracing = DBG && MJV_TRACE_EPI && args.trace != nullptr && blockIdx.x == 0 && warp == 8 && lane == 0;
         [[maybe_unused]] int n_tr = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const Item t = decode_item<CAUSAL>(args, it);
+            if constexpr (KVT) {
+                if (args.kv_tail != 0) {
+                    // V row of the trailing key, one element per thread (tile r / 64, dim r % 64), shared through sVT
+                    const int tv = r >> 6, dv = r & 63;
+                    float vt = 0.f;
+                    if (sel2(tv, t.nblk) > 0)
+                        vt = __bfloat162float(args.vt_ptr[static_cast<long long>(t.v_plane + (t.dual ? tv : 0)) * args.vt_plane_stride +
+                                                          static_cast<long long>(dv) * args.vt_ld + t.v_col0 + t.len - 1]);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");   // the previous item's reads of sVT are done
+                    sVT[tv * HD + dv] = vt;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+            }
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
                 if (t.nblk[tt] == 0) continue;
@@ -613,6 +696,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const bool warp_has_rows = (t.q0[tt] + qw * 32) < t.len;
                 if (warp_has_rows) {
                     const float inv = 1.0f / sL[tt * BQ + r];
+                    [[maybe_unused]] float p_tail = 0.f;
+                    if constexpr (KVT) p_tail = sPT[tt * BQ + r];
                     // One thread owns one row in TMEM: a store instruction writes 16 bytes of 32 different rows. A variant that
                     // transposed 4 x 4 quads inside lane groups (8 rows x 64 contiguous bytes per instruction) measured no
                     // faster: the drain (2500-4500 cycles per tile, tools/attn_trace.py with -DMJV_TRACE_EPI=1) is bound by
@@ -626,6 +711,19 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         uint32_t o[32];
                         ptx::tmem_ld_x32(tmem_O + c * 32, o);
                         ptx::tmem_wait_ld();
+                        if constexpr (KVT) {
+                            if (args.kv_tail != 0) {   // + p_last * v_last (fp32, before the normalisation)
+                                const float4* v4 = reinterpret_cast<const float4*>(sVT + tt * HD + c * 32);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 vv = v4[i];
+                                    o[4 * i + 0] = __float_as_uint(fmaf(p_tail, vv.x, __uint_as_float(o[4 * i + 0])));
+                                    o[4 * i + 1] = __float_as_uint(fmaf(p_tail, vv.y, __uint_as_float(o[4 * i + 1])));
+                                    o[4 * i + 2] = __float_as_uint(fmaf(p_tail, vv.z, __uint_as_float(o[4 * i + 2])));
+                                    o[4 * i + 3] = __float_as_uint(fmaf(p_tail, vv.w, __uint_as_float(o[4 * i + 3])));
+                                }
+                            }
+                        }
                         if (qrow < t.len) {
                             uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
@@ -647,7 +745,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
         }
     } else {
-        ptx::setmaxnreg_dec<64>();
+        ptx::setmaxnreg_dec<56>();
         if (warp == 12) {
             // ===================================================== TMA producer
             if (ptx::elect_one()) {
@@ -671,32 +769,35 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     }
                     for (int j = 0; j < t.nblk_max; ++j) {
                         if constexpr (DBG) dbg_aux = (static_cast<long long>(it) << 32) | (static_cast<long long>(j) << 16) | (vst << 8) | vph;
-                        wait_sp(&k_empty[kst], kph ^ 1, 11);
-                        ptx::mbar_expect_tx(&k_full[kst], L::kKBytes);
+                        // a dual item streams K/V of head h for tile 0, then of head h + 1 for tile 1, block by block
+                        for (int s = 0; s <= t.dual; ++s) {
+                            wait_sp(&k_empty[kst], kph ^ 1, 11);
+                            ptx::mbar_expect_tx(&k_full[kst], L::kKBytes);
 #pragma unroll
-                        for (int kd = 0; kd < HD / 64; ++kd)
-                            ptx::tma_load_3d(sK + kst * L::kKBytes + kd * (BKV * 128), &tmK, &k_full[kst],
-                                             args.k_col0 + t.kvh * HD + kd * 64, t.tma_row0 + j * BKV, t.tma_batch,
-                                             ptx::kEvictLast);
-                        if (++kst == KS) { kst = 0; kph ^= 1; }
-                        if constexpr (KS == 1) {
-                            // single K stage: the next block's load can only be issued when S of this one has retired - pull
-                            // it into L2 now, so that load costs an L2 hit (~700 cycles) and not an HBM round trip (~2200,
-                            // tools/attn_trace.py: score waits of 1250 cycles per step whenever K came from HBM)
-                            if (j + 1 < t.nblk_max) {
+                            for (int kd = 0; kd < HD / 64; ++kd)
+                                ptx::tma_load_3d(sK + kst * L::kKBytes + kd * (BKV * 128), &tmK, &k_full[kst],
+                                                 args.k_col0 + (t.kvh + s) * HD + kd * 64, t.tma_row0 + j * BKV, t.tma_batch,
+                                                 ptx::kEvictLast);
+                            if (++kst == KS) { kst = 0; kph ^= 1; }
+                            if constexpr (KS == 1) {
+                                // single K stage: the next block's load can only be issued when S of this one has retired -
+                                // pull it into L2 now, so that load costs an L2 hit (~700 cycles) and not an HBM round trip
+                                // (~2200, tools/attn_trace.py: score waits of 1250 cycles per step whenever K came from HBM)
+                                if (j + 1 < t.nblk_max && !t.dual) {
 #pragma unroll
-                                for (int kd = 0; kd < HD / 64; ++kd)
-                                    ptx::tma_prefetch_3d(&tmK, args.k_col0 + t.kvh * HD + kd * 64, t.tma_row0 + (j + 1) * BKV,
-                                                         t.tma_batch);
+                                    for (int kd = 0; kd < HD / 64; ++kd)
+                                        ptx::tma_prefetch_3d(&tmK, args.k_col0 + t.kvh * HD + kd * 64,
+                                                             t.tma_row0 + (j + 1) * BKV, t.tma_batch);
+                                }
                             }
-                        }
-                        wait_sp(&v_empty[vst], vph ^ 1, 12);
-                        ptx::mbar_expect_tx(&v_full[vst], L::kVBytes);
+                            wait_sp(&v_empty[vst], vph ^ 1, 12);
+                            ptx::mbar_expect_tx(&v_full[vst], L::kVBytes);
 #pragma unroll
-                        for (int half = 0; half < 2; ++half)
-                            ptx::tma_load_3d(sV + vst * L::kVBytes + half * (HD * 128), &tmV, &v_full[vst],
-                                             t.v_col0 + j * BKV + half * 64, 0, t.v_plane, ptx::kEvictLast);
-                        if (++vst == VS) { vst = 0; vph ^= 1; }
+                            for (int half = 0; half < 2; ++half)
+                                ptx::tma_load_3d(sV + vst * L::kVBytes + half * (HD * 128), &tmV, &v_full[vst],
+                                                 t.v_col0 + j * BKV + half * 64, 0, t.v_plane + s, ptx::kEvictLast);
+                            if (++vst == VS) { vst = 0; vph ^= 1; }
+                        }
                     }
                 }
             }
@@ -719,18 +820,18 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             uint32_t p_ph = 0;
             uint32_t o_use[2] = {0, 0};
             [[maybe_unused]] uint32_t p_use[2] = {0, 0};   // P-in-smem mode: steps of each tile so far (p_full[tt] phases)
-            const bool tracing = args.trace != nullptr && blockIdx.x == 0 && leader;
+            const bool tracing = DBG && args.trace != nullptr && blockIdx.x == 0 && leader;
             int n_tr = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const ItemLite t = decode_lite<CAUSAL>(args, it);
                 for (int j = 0; j < t.nblk_max; ++j) {
-                    const uint64_t vb0 = v_desc0 + static_cast<uint64_t>((vst * L::kVBytes) >> 4);
 #pragma unroll 1
                     for (int tt = 0; tt < 2; ++tt) {  // one copy of the code: the issuer's instruction footprint matters
                         if (!(j < sel2(tt, t.nblk))) continue;
                         if constexpr (DBG) dbg_aux = (static_cast<long long>(it) << 32) | (static_cast<long long>(g) << 8) | (p_sb << 4) | p_ph;
-                        const bool first_of_block = (tt == 0) || !(j < t.nblk[0]);
-                        const bool last_of_block = (tt == 1) || !(j < t.nblk[1]);
+                        const uint64_t vb0 = v_desc0 + static_cast<uint64_t>((vst * L::kVBytes) >> 4);
+                        const bool first_of_block = t.dual || (tt == 0) || !(j < t.nblk[0]);
+                        const bool last_of_block = t.dual || (tt == 1) || !(j < t.nblk[1]);
                         const bool last_of_tile = j == sel2(tt, t.nblk) - 1;
                         // waits that are normally satisfied long before P arrives come first: off the critical path
                         if (first_of_block) wait_sp(&v_full[vst], vph, 20);
@@ -794,18 +895,18 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             int sb = 0;               // score buffer of the next S step
             uint32_t sph = 0;         // parity of its CURRENT use; its previous use completed pv_done[sb] in phase sph ^ 1
             bool wrapped = false;     // every buffer has been used once
-            const bool tracing = !MJV_TRACE_EPI && args.trace != nullptr && blockIdx.x == 0 && leader;
+            const bool tracing = DBG && !MJV_TRACE_EPI && args.trace != nullptr && blockIdx.x == 0 && leader;
             int n_tr = 0;
             int gs = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const ItemLite t = decode_lite<CAUSAL>(args, it);
                 for (int j = 0; j < t.nblk_max; ++j) {
-                    const uint64_t b0 = k_desc0 + static_cast<uint64_t>((kst * L::kKBytes) >> 4);
 #pragma unroll 1
                     for (int tt = 0; tt < 2; ++tt) {
                         if (!(j < sel2(tt, t.nblk))) continue;
-                        const bool first_of_block = (tt == 0) || !(j < t.nblk[0]);
-                        const bool last_of_block = (tt == 1) || !(j < t.nblk[1]);
+                        const uint64_t b0 = k_desc0 + static_cast<uint64_t>((kst * L::kKBytes) >> 4);
+                        const bool first_of_block = t.dual || (tt == 0) || !(j < t.nblk[0]);
+                        const bool last_of_block = t.dual || (tt == 1) || !(j < t.nblk[1]);
                         const bool last_of_tile = j == sel2(tt, t.nblk) - 1;
                         const uint32_t use = sel2(tt, q_use);
                         const int buf = (use % QSETS) * 2 + tt;

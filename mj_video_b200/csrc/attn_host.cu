@@ -122,8 +122,17 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
         a.pair_heads = (varlen && a.kv_group % 2 == 0) ? 1 : 0;
         if (const char* tp = getenv("MJV_ATTN_TRACE"))  // tools/attn_trace.py: device pointer (hex) of the event buffer
             a.trace = reinterpret_cast<long long*>(strtoull(tp, nullptr, 16));
+        // single trailing key on the CUDA cores; needs more key blocks than score buffers (see the q_full wait in the kernel)
+        a.kv_tail = (!varlen && !d.causal && hd == 64 && v_hd == hd && d.seq_len % 128 == 1 && d.seq_len > 4 * 128) ? 1 : 0;
+        a.k_ptr = static_cast<const __nv_bfloat16*>(d.k);
+        a.ldk = d.ldk;
+        a.vt_ptr = static_cast<const __nv_bfloat16*>(d.vt);
+        a.vt_ld = d.vt_ld;
+        a.vt_plane_stride = d.vt_plane_stride;
+        a.pair_tail = (!varlen && (n_qblocks & 1) && d.heads % 2 == 0 && d.heads == d.kv_heads) ? 1 : 0;
         const long long n2 = varlen ? (long long)d.n_work * (a.pair_heads ? d.heads / 2 : d.heads)
-                                    : (long long)d.nseq * d.heads * ((n_qblocks + 1) / 2);
+                             : a.pair_tail ? (long long)d.nseq * (d.heads * (n_qblocks / 2) + d.heads / 2)
+                                           : (long long)d.nseq * d.heads * ((n_qblocks + 1) / 2);
         MJV_CHECK(n2 > 0 && n2 < (1LL << 31), MJV_ERR_ARG, "attention: bad item count %lld", n2);
         a.n_items = (int)n2;
         a.n_qblocks = n_qblocks;

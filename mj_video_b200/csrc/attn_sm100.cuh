@@ -43,6 +43,15 @@ struct AttnArgs {
     int batched;            // 1: maps carry a per-sequence batch dim and rows are sequence-relative (ViT)
     int out_hd;             // columns per head written to `out` (<= HD, multiple of 16): narrow heads are stored packed
     int pair_heads;         // attention2 (attn2_sm100.cuh), varlen: the two query tiles of an item are the heads 2p, 2p+1
+    int pair_tail;          // attention2, batched, odd q-block count (ViT: 1025 = 8 x 128 + 1): the last q-blocks of heads 2p, 2p+1
+                            // share an item (each tile with its OWN K/V stream) instead of running as two one-tile items
+    int kv_tail;            // attention2, batched bidirectional head_dim 64, seq_len % 128 == 1 (ViT: 1025): the last key is folded
+                            // in on the CUDA cores (softmax warps: q.k_last; epilogue: + p_last * v_last) instead of costing
+                            // every item a ninth 128-column step with one valid column
+    const __nv_bfloat16* k_ptr;    // raw K / V^T pointers for that path (same tensors the maps describe)
+    long long ldk;
+    const __nv_bfloat16* vt_ptr;
+    long long vt_ld, vt_plane_stride;
     long long* trace;       // attention2, tools only: CTA 0 records (clock64, tag<<32|step) pairs per role here (or nullptr)
 };
 

@@ -195,6 +195,33 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
         rows = 1;
     }
     if (ends_with(key, "language_model.output.weight")) return 0;  // LM head: never used by the reward path
+    // Phi-3 checkpoints (InternVL2-4B, /root/reference/README.md:18) ship q|k|v and gate|up as single matrices
+    // (transformers Phi3Attention.qkv_proj: rows [q heads | k heads | v heads]; Phi3MLP.gate_up_proj: rows [gate | up], chunk(2)).
+    // Row ranges of a row-major matrix are contiguous: hand them on under the separate Llama-style names.
+    {
+        const std::string raw(key_c);
+        const size_t esz = dtype_size(dtype);
+        const char* bytes = static_cast<const char*>(data);
+        const auto sub = [&](const std::string& from, const std::string& to, long long r0, long long nr) {
+            std::string k2 = raw;
+            replace_all(k2, from, to);
+            int64_t shp[2] = {nr, cols};
+            return load_weight(h, k2.c_str(), bytes + static_cast<size_t>(r0) * cols * esz, shp, 2, dtype);
+        };
+        if (ends_with(raw, ".self_attn.qkv_proj.weight")) {
+            const long long hd_ = c.llm_hidden / c.llm_heads, nq = c.llm_heads * hd_, nk = c.llm_kv_heads * hd_;
+            MJV_CHECK(ndim == 2 && rows == nq + 2 * nk, MJV_ERR_ARG, "%s: %lld rows, expected %lld", key_c, rows, nq + 2 * nk);
+            MJV_PROPAGATE(sub(".qkv_proj.", ".q_proj.", 0, nq));
+            MJV_PROPAGATE(sub(".qkv_proj.", ".k_proj.", nq, nk));
+            return sub(".qkv_proj.", ".v_proj.", nq + nk, nk);
+        }
+        if (ends_with(raw, ".mlp.gate_up_proj.weight")) {
+            MJV_CHECK(ndim == 2 && rows == 2LL * c.llm_inter, MJV_ERR_ARG, "%s: %lld rows, expected %lld", key_c, rows,
+                      2LL * c.llm_inter);
+            MJV_PROPAGATE(sub(".gate_up_proj.", ".gate_proj.", 0, c.llm_inter));
+            return sub(".gate_up_proj.", ".up_proj.", c.llm_inter, c.llm_inter);
+        }
+    }
     const long long n_elem = rows * cols;
     h->finalized = false;
     if (c.precision == 1) return load_weight_f32(h, key, data, rows, cols, dtype);  // verification mode: no re-packing

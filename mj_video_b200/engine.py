@@ -11,6 +11,7 @@ Index semantics are the reference's:
 from __future__ import annotations
 
 import ctypes as C
+import math
 import warnings
 from dataclasses import dataclass
 
@@ -91,6 +92,11 @@ class EngineDims:
     rope_scaling_factor: float | None = 2.0   # InternLM2 rope_scaling {'type': 'dynamic', 'factor': f}; None = no scaling
     ps_version: int = 2                        # 1 = 'v1' pixel-shuffle layout (transposed token grid)
     rope_scaling_type: str = "dynamic"         # 'dynamic' (NTK re-basing beyond max_pos) or 'linear' (positions / factor)
+    # Phi-3 LongRoPE (rope_scaling {'type': 'su' | 'longrope', 'short_factor': [...], 'long_factor': [...]}; Llama-layout
+    # branch only): per-frequency divisors, the long set once a batch is longer than the original context
+    rope_short_factor: tuple | None = None
+    rope_long_factor: tuple | None = None
+    rope_original_max_pos: int | None = None
 
     @staticmethod
     def from_synth(d) -> "EngineDims":
@@ -106,7 +112,13 @@ class EngineDims:
             aspect2criteria={k: list(v) for k, v in d.aspect2criteria.items()}, downsample_ratio=d.downsample_ratio,
             rope_scaling_factor=getattr(d, "rope_scaling_factor", 2.0),
             ps_version=1 if getattr(d, "ps_version", "v2") == "v1" else 2,
-            rope_scaling_type=getattr(d, "rope_scaling_type", "dynamic"))
+            rope_scaling_type=getattr(d, "rope_scaling_type", "dynamic"),
+            rope_short_factor=getattr(d, "rope_short_factor", None), rope_long_factor=getattr(d, "rope_long_factor", None),
+            rope_original_max_pos=getattr(d, "rope_original_max_pos", None))
+
+    @property
+    def longrope(self) -> bool:
+        return self.llm_arch == 1 and self.rope_scaling_type in ("su", "longrope") and self.rope_short_factor is not None
 
     @property
     def vit_seq(self) -> int:
@@ -126,6 +138,21 @@ def applied_vit_layers(n_layers: int, select_layer: int) -> int:
     if not 0 < k <= n_layers:
         raise ValueError(f"select_layer={select_layer} is outside the {n_layers}-layer vision encoder")
     return k
+
+
+def longrope_inv_freq(d: "EngineDims", hd: int, seq_len: int):
+    """Phi-3 LongRoPE (transformers `_compute_longrope_parameters` / Phi3LongRoPEScaledRotaryEmbedding): inverse frequencies
+    divided by `long_factor` when the call is longer than the original context, else by `short_factor`; cos/sin scaled by
+    sqrt(1 + ln(max_pos / original) / ln(original)) when the context was extended. Returns (inv_freq fp32, scale, long?)."""
+    orig = int(d.rope_original_max_pos or d.max_pos)
+    use_long = seq_len > orig
+    ext = torch.tensor(d.rope_long_factor if use_long else d.rope_short_factor, dtype=torch.float32)
+    if ext.numel() != hd // 2:
+        raise ValueError(f"LongRoPE factor lists need head_dim/2 = {hd // 2} entries, got {ext.numel()}")
+    inv_freq = 1.0 / (ext * d.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+    scale = d.max_pos / orig
+    mscale = 1.0 if scale <= 1.0 else math.sqrt(1.0 + math.log(scale) / math.log(orig))
+    return inv_freq, mscale, use_long
 
 
 _DTYPES = {torch.float32: _lib.MJV_DTYPE_F32, torch.bfloat16: _lib.MJV_DTYPE_BF16, torch.float16: _lib.MJV_DTYPE_F16}
@@ -182,7 +209,7 @@ class Engine:
             pass
 
     # -------------------------------------------------------------------------------------------- weights
-    def _load_rope(self, seq_len: int | None = None):
+    def _load_rope(self, seq_len: int | None = None, call_len: int = 0):
         """cos/sin tables as the reference's rotary modules produce them in a bf16 model, one column per rotary pair of
         the 128-wide head slot the kernels use (pairs beyond head_dim/2 are padding: cos 1, sin 0).
         InternLM2 (modeling_internlm2.py:147-180): fp32 tables for max_position_embeddings rows built at init, cast with
@@ -209,7 +236,10 @@ class Engine:
                 f = d.rope_scaling_factor
                 base = base * ((f * rows / d.max_pos) - (f - 1)) ** (hd / (hd - 2))
         inv_freq = 1.0 / (base ** (torch.arange(0, hd, 2).float() / hd))
-        if d.llm_arch == 1 and self.rope_inv_freq_bf16:
+        mscale = 1.0
+        if d.longrope:
+            inv_freq, mscale, self._rope_long = longrope_inv_freq(d, hd, call_len)   # factor set by the CALL's length
+        elif d.llm_arch == 1 and self.rope_inv_freq_bf16:
             inv_freq = inv_freq.to(torch.bfloat16).float()
         t = torch.arange(rows, dtype=inv_freq.dtype)
         if linear:
@@ -218,19 +248,22 @@ class Engine:
         cos = torch.ones((rows, 64), dtype=torch.float32)
         sin = torch.zeros((rows, 64), dtype=torch.float32)
         if self.fp32:   # a float32 model keeps the tables as computed (modeling_internlm2.py:166-170 casts to the model dtype)
-            cos[:, : hd // 2] = freqs.cos()
-            sin[:, : hd // 2] = freqs.sin()
+            cos[:, : hd // 2] = freqs.cos() * mscale
+            sin[:, : hd // 2] = freqs.sin() * mscale
         else:
-            cos[:, : hd // 2] = freqs.cos().to(torch.bfloat16).to(torch.float32)
-            sin[:, : hd // 2] = freqs.sin().to(torch.bfloat16).to(torch.float32)
+            cos[:, : hd // 2] = (freqs.cos() * mscale).to(torch.bfloat16).to(torch.float32)
+            sin[:, : hd // 2] = (freqs.sin() * mscale).to(torch.bfloat16).to(torch.float32)
         self.load_weight("rope.cos", cos)
         self.load_weight("rope.sin", sin)
         self._rope_rows = rows
 
     def _ensure_rope(self, padded_len: int):
-        """The reference looks at kv_seq_len = the PADDED batch length (modeling_internlm2.py:172-175, 380)."""
-        if padded_len > self._rope_rows:
-            self._load_rope(seq_len=padded_len)
+        """The reference looks at kv_seq_len = the PADDED batch length (modeling_internlm2.py:172-175, 380). LongRoPE picks
+        its factor set per call from that length, so crossing the original context in either direction rebuilds the table."""
+        d = self.dims
+        flip = d.longrope and (padded_len > (d.rope_original_max_pos or d.max_pos)) != getattr(self, "_rope_long", False)
+        if padded_len > self._rope_rows or flip:
+            self._load_rope(seq_len=max(padded_len, self._rope_rows) if d.longrope else padded_len, call_len=padded_len)
             self.finalize()
 
     def load_weight(self, key: str, tensor: torch.Tensor):

@@ -50,7 +50,10 @@ class ModelDims:
     rope_theta: float = 1000000.0
     max_pos: int = 32768
     rope_scaling_factor: float | None = 2.0   # rope_scaling {'type': 'dynamic', 'factor': 2.0} (InternLM2 branch only)
-    rope_scaling_type: str = "dynamic"        # or 'linear' (modeling_internlm2.py:318-333)
+    rope_scaling_type: str = "dynamic"        # or 'linear' (modeling_internlm2.py:318-333); 'longrope' on the Llama-layout branch
+    rope_short_factor: tuple | None = None    # Phi-3 LongRoPE (InternVL2-4B): per-frequency divisors, head_dim/2 entries each
+    rope_long_factor: tuple | None = None
+    rope_original_max_pos: int | None = None
     # projector
     downsample_ratio: float = 0.5
     select_layer: int = -1        # ViT hidden state fed to the projector (modeling_internvl_chat.py:244-254)

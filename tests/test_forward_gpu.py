@@ -584,3 +584,72 @@ def test_reference_collator_padding_convention_gives_identical_bits(tiny_engine,
     mask3072[:, : mask.shape[1]] = mask
     b = eng.forward(pv, ids3072, mask3072, synth.PAD, synth.IMG_CONTEXT)["scores"]
     assert torch.equal(a, b)
+
+
+def test_phi3_fused_weights_and_longrope(gpu):
+    """N4: a Phi-3 style checkpoint (qkv_proj / gate_up_proj, /root/reference/README.md:18) loads into the same packed weights
+    as the separate Llama-style keys - scores bit-identical - and LongRoPE tables follow the call length (short factors up to
+    the original context, long factors beyond), each checked against the oracle given the same cos/sin."""
+    import dataclasses
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from mj_video_b200.engine import Engine, EngineDims
+    d = synth.dims_tiny_llama()
+    sd = synth.make_state_dict(d, seed=11, include_lm_head=False)
+    fused = {}
+    for k, v in sd.items():
+        if ".self_attn.q_proj." in k:
+            base = k.replace(".q_proj.", ".{}.")
+            fused[k.replace(".q_proj.", ".qkv_proj.")] = torch.cat([v, sd[base.format("k_proj")], sd[base.format("v_proj")]])
+        elif ".mlp.gate_proj." in k:
+            fused[k.replace(".gate_proj.", ".gate_up_proj.")] = torch.cat([v, sd[k.replace(".gate_proj.", ".up_proj.")]])
+        elif any(t in k for t in (".k_proj.", ".v_proj.", ".up_proj.")):
+            continue
+        else:
+            fused[k] = v
+    assert any("qkv_proj" in k for k in fused) and not any(".q_proj." in k for k in fused)
+    pv = torch.cat([load_video(synth.make_video(40 + i), num_segments=8, max_num=1)[0] for i in range(2)]).cuda().bfloat16()
+    ids, mask = synth.pad_batch([synth.make_input_ids(i, [1] * 8, n_cap=n) for i, n in enumerate([9, 40])])
+    outs = []
+    for state in (sd, fused):
+        for prec in ("bf16", "fp32"):
+            eng = Engine(EngineDims.from_synth(d), gpu, precision=prec)
+            eng.load_state_dict(state)
+            x = pv if prec == "bf16" else pv.float()
+            outs.append(eng.forward(x, ids, mask, synth.PAD, synth.IMG_CONTEXT)["scores"].float().cpu())
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+    # a wrong row count is refused
+    eng = Engine(EngineDims.from_synth(d), gpu)
+    from mj_video_b200._lib import MjvError
+    k = next(k for k in fused if "qkv_proj" in k)
+    with pytest.raises(MjvError):
+        eng.load_weight(k, fused[k][:-1])
+    # LongRoPE: the table switches factor sets with the padded call length, in both directions; oracle restates transformers
+    from oracle import port
+    hd = d.llm_hidden // d.llm_heads
+    g = torch.Generator().manual_seed(1)
+    dl = dataclasses.replace(d, rope_scaling_type="longrope", rope_original_max_pos=int(ids.shape[1]) + 8, max_pos=4 * d.max_pos,
+                             rope_short_factor=tuple((1.0 + 0.2 * torch.rand(hd // 2, generator=g)).tolist()),
+                             rope_long_factor=tuple((1.5 + 4.0 * torch.rand(hd // 2, generator=g)).tolist()))
+    eng = Engine(EngineDims.from_synth(dl), gpu)
+    eng.load_state_dict(sd)
+    orc = port.Oracle(dl, sd, dtype=torch.bfloat16, device=gpu)
+    NO, NA = d.num_objectives, d.num_aspects
+
+    def table(o):
+        return torch.cat([o["rewards"].float(), o["aspect_scores"].float(), o["score"].float()[:, None]], 1).cpu()
+
+    short1 = eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT)["scores"].float().cpu()
+    assert not eng._rope_long
+    assert (short1 - table(orc.forward(pv, ids, mask))).abs().max().item() <= 2e-2
+    ids_l = torch.nn.functional.pad(ids, (0, 16), value=synth.PAD)
+    mask_l = torch.nn.functional.pad(mask, (0, 16), value=0)
+    long1 = eng.forward(pv, ids_l, mask_l, synth.PAD, synth.IMG_CONTEXT)["scores"].float().cpu()
+    assert eng._rope_long
+    assert (long1 - table(orc.forward(pv, ids_l, mask_l))).abs().max().item() <= 2e-2
+    short2 = eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT)["scores"].float().cpu()
+    assert not eng._rope_long and torch.equal(short1, short2)
+    assert not torch.equal(short1, long1)          # different frequencies -> different hidden states
+    plain = Engine(EngineDims.from_synth(d), gpu)
+    plain.load_state_dict(sd)
+    assert not torch.equal(plain.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT)["scores"].float().cpu(), short1)

@@ -472,3 +472,38 @@ def test_clip_decode_pool_matches_serial_decode(tmp_path):
     assert arr[0].shape == (4, 32, 48, 3)
     with ClipDecodePool(workers=2, num_segments=4) as pool, pytest.raises(Exception):
         list(pool.map([paths[0], str(tmp_path / "missing.avi")]))
+
+
+def test_longrope_tables_match_transformers():
+    """N4 (Phi-3 / InternVL2-4B LongRoPE): the factor-set choice, inverse frequencies and the attention scale agree with
+    transformers' own `_compute_longrope_parameters` (the implementation the reference's Llama-layout branch would call)."""
+    import types
+    import torch
+    from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
+    from mj_video_b200 import synth
+    from mj_video_b200.engine import EngineDims, longrope_inv_freq
+    d0 = synth.dims_tiny_llama()
+    hd = d0.llm_hidden // d0.llm_heads
+    g = torch.Generator().manual_seed(0)
+    short = (1.0 + 0.1 * torch.rand(hd // 2, generator=g)).tolist()
+    long_ = (1.0 + 30.0 * torch.rand(hd // 2, generator=g)).tolist()
+    import dataclasses
+    d = dataclasses.replace(EngineDims.from_synth(d0), rope_scaling_type="longrope", rope_short_factor=tuple(short),
+                            rope_long_factor=tuple(long_), rope_original_max_pos=64, max_pos=2048)
+    assert d.longrope
+    cfg = types.SimpleNamespace(
+        hidden_size=d.llm_hidden, num_attention_heads=d.llm_heads, max_position_embeddings=d.max_pos,
+        rope_parameters=dict(rope_type="longrope", rope_theta=d.rope_theta, short_factor=short, long_factor=long_,
+                             original_max_position_embeddings=64))
+    cfg.standardize_rope_params = lambda: None
+    for seq_len, want_long in ((10, False), (64, False), (65, True), (2000, True)):
+        inv, scale, is_long = longrope_inv_freq(d, hd, seq_len)
+        ref_inv, ref_scale = ROPE_INIT_FUNCTIONS["longrope"](cfg, None, seq_len=seq_len)
+        assert is_long == want_long
+        assert torch.equal(inv, ref_inv) and abs(scale - ref_scale) < 1e-12 and scale > 1.0
+    # no extension of the context -> no scale
+    d1 = dataclasses.replace(d, max_pos=64)
+    assert longrope_inv_freq(d1, hd, 10)[1] == 1.0
+    import pytest
+    with pytest.raises(ValueError):
+        longrope_inv_freq(dataclasses.replace(d, rope_short_factor=(1.0,)), hd, 10)

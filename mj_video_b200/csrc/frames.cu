@@ -158,8 +158,22 @@ AxisCoeffs make_coeffs(int in_size, int out_size) {
 
 struct DeviceCoeffs {
     int ksize = 0;
+    int out_size = 0;
     int* bounds = nullptr;
     int* kk = nullptr;
+    const std::vector<int>* host_bounds = nullptr;   // [out][2], owned by the cache
+
+    // largest number of input samples any block of `block` consecutive outputs reads (first tap of its first output to
+    // the last tap of its last output)
+    int max_span(int block) const {
+        int best = 0;
+        const std::vector<int>& b = *host_bounds;
+        for (int o0 = 0; o0 < out_size; o0 += block) {
+            const int o1 = std::min(out_size, o0 + block) - 1;
+            best = std::max(best, b[2 * o1] + b[2 * o1 + 1] - b[2 * o0]);
+        }
+        return best;
+    }
 };
 
 // geometry cache: coefficient tables depend only on (in,out) per axis and are kept per device. Library-owned device memory, never freed.
@@ -176,6 +190,8 @@ int get_device_coeffs(int in_size, int out_size, cudaStream_t st, DeviceCoeffs* 
     AxisCoeffs c = make_coeffs(in_size, out_size);
     DeviceCoeffs d;
     d.ksize = c.ksize;
+    d.out_size = out_size;
+    d.host_bounds = new std::vector<int>(c.bounds);   // library-owned like the device tables
     MJV_CUDA_OK(cudaMalloc(&d.bounds, c.bounds.size() * sizeof(int)));
     MJV_CUDA_OK(cudaMalloc(&d.kk, c.kk.size() * sizeof(int)));
     MJV_CUDA_OK(cudaMemcpyAsync(d.bounds, c.bounds.data(), c.bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -252,6 +268,225 @@ resample_v_tiles_kernel(const uint8_t* __restrict__ tmp, TOut* __restrict__ out,
     }
 }
 
+
+// Fused resize: one CTA produces a BW x BH block of the resized frame. The horizontal pass runs over just the input rows
+// the block's vertical taps read and keeps its uint8 result (Pillow's intermediate image, same rounding) in shared memory;
+// the vertical pass, crop, LUT and planar store follow in the same CTA - the [F,H,OW,3] temporary never exists in HBM.
+//   stage:   32 input rows per pass, copied with aligned 4-byte loads and shifted so that every staged row starts on a word;
+//   phase 1: lane = row, warp = output column. The taps of one output pixel are 3n contiguous bytes; they are read as
+//            words (4 taps = 3 words after a warp-uniform funnel shift) and the bytes picked with PRMT - a byte load per tap
+//            and channel made the first version of this kernel shared-memory-issue bound (tools/frames_bench.py: 1.77 ms
+//            for 256 x 720p). Coefficients come 4 at a time (one 16-byte broadcast load). Lanes hit 32 different banks
+//            (row stride = 4 mod 128 bytes);
+//   phase 2: vertical taps on 4 interleaved bytes (one word) per thread;
+//   phase 3: LUT + planar stores with lane = output column inside one colour plane (contiguous 2/4-byte elements).
+// Work: 3 * (ksize_h * rows_read / BH + ksize_v) integer MACs per output pixel against ~(3*W*H/(OW*OH) + 3*sizeof(TOut)) bytes:
+// 1280x720 -> 448x448 is 20 M MACs (+ as many byte extractions) per 4 MB of traffic. The integer pipe, not HBM, bounds
+// this kernel for real video sizes (frame path).
+struct FusedGeom {
+    int F, H, W, OW, OH, S, gi, tiles_per_frame, tile_offset;
+    int BW, BH, ksh, ksh4, ksv;
+    int stage_stride;   // bytes per staged input row (multiple of 4, = 4 mod 128)
+    int stage_bytes;    // staging area (also holds the BH x 3*BW output bytes between phases 2 and 3)
+    int rmax;           // rows of hbuf
+    long long in_bytes;
+    const int *bounds_h, *kk_h, *bounds_v, *kk_v;
+};
+constexpr int kFusedBW = 64;       // output columns per CTA
+constexpr int kHbufStride = 196;   // 64 pixels x 3 bytes + 4: 49 words, odd -> conflict-free across rows
+
+__device__ __forceinline__ uint32_t load_word_guarded(const uint8_t* p, const uint8_t* end) {
+    if (p + 4 <= end) return __ldg(reinterpret_cast<const uint32_t*>(p));
+    uint32_t v = 0;
+    for (int b = 0; b < 4; ++b)
+        if (p + b < end) v |= static_cast<uint32_t>(p[b]) << (8 * b);
+    return v;
+}
+template <int B>
+__device__ __forceinline__ int byte_of(uint32_t w) { return static_cast<int>(__byte_perm(w, 0, 0x4440 | B)); }
+
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+resample_fused_kernel(const uint8_t* __restrict__ in, TOut* __restrict__ out, const FusedGeom g, const NormLut lut_arg) {
+    extern __shared__ __align__(16) uint8_t fsm[];
+    float* lut = reinterpret_cast<float*>(fsm);                       // [768]
+    int* kh = reinterpret_cast<int*>(fsm + 3072);                     // [BW][ksh4], zero padded
+    int* kv = kh + g.BW * g.ksh4;                                     // [BH][ksv]
+    int* bh = kv + g.BH * g.ksv;                                      // [BW][2]
+    int* bv = bh + 2 * g.BW;                                          // [BH][2]
+    uint8_t* hbuf = reinterpret_cast<uint8_t*>(bv + 2 * g.BH);        // [rmax][kHbufStride]
+    uint8_t* stage = hbuf + ((g.rmax * kHbufStride + 15) & ~15);      // [32][stage_stride]
+
+    const int nbx = (g.OW + g.BW - 1) / g.BW, nby = (g.OH + g.BH - 1) / g.BH;
+    const int bx = blockIdx.x % nbx;
+    const int by = (blockIdx.x / nbx) % nby;
+    const long long f = blockIdx.x / (nbx * nby);
+    const int gx0 = bx * g.BW, gy0 = by * g.BH;
+    const int bw = min(g.BW, g.OW - gx0), bhh = min(g.BH, g.OH - gy0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < 768; i += 256) lut[i] = lut_arg.v[i];
+    for (int i = tid; i < bw * g.ksh4; i += 256) {
+        const int ox = i / g.ksh4, x = i - ox * g.ksh4;
+        kh[i] = x < g.ksh ? g.kk_h[static_cast<long long>(gx0 + ox) * g.ksh + x] : 0;
+    }
+    for (int i = tid; i < bhh * g.ksv; i += 256) kv[i] = g.kk_v[static_cast<long long>(gy0) * g.ksv + i];
+    for (int i = tid; i < 2 * bw; i += 256) bh[i] = g.bounds_h[2 * gx0 + i];
+    for (int i = tid; i < 2 * bhh; i += 256) bv[i] = g.bounds_v[2 * gy0 + i];
+    __syncthreads();
+    const int x_lo = bh[0], x_hi = bh[2 * (bw - 1)] + bh[2 * (bw - 1) + 1];
+    const int y_lo = bv[0], y_hi = bv[2 * (bhh - 1)] + bv[2 * (bhh - 1) + 1];
+    const int seg_words = ((x_hi - x_lo) * 3 + 3) >> 2;
+    const int rows = y_hi - y_lo;
+    const uint8_t* frame = in + f * g.H * static_cast<long long>(g.W) * 3;
+    const uint8_t* in_end = in + g.in_bytes;
+
+    for (int r0 = 0; r0 < rows; r0 += 32) {
+        // ---- stage up to 32 input row segments: warp w copies rows w, w+8, ... and shifts them onto a word boundary.
+        // All loads of a 256-word chunk are issued before the first store (the copy is latency bound otherwise); only the
+        // last row of the whole input can touch the end of the allocation and takes the guarded loads.
+        for (int r = warp; r < 32 && r0 + r < rows; r += 8) {
+            const uint8_t* src = frame + (static_cast<long long>(y_lo + r0 + r) * g.W + x_lo) * 3;
+            const int lead = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 3);
+            const uint8_t* src_al = src - lead;
+            uint32_t* dst4 = reinterpret_cast<uint32_t*>(stage + r * g.stage_stride);
+            if (src_al + 4 * (seg_words + 1) <= in_end) {
+                const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src_al);
+                for (int base = 0; base < seg_words; base += 256) {
+                    uint32_t lo[8], hi[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = base + u * 32 + lane;
+                        if (i < seg_words) {
+                            lo[u] = __ldg(s4 + i);
+                            hi[u] = __ldg(s4 + i + 1);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = base + u * 32 + lane;
+                        if (i < seg_words) dst4[i] = __funnelshift_r(lo[u], hi[u], 8 * lead);
+                    }
+                }
+            } else {
+                for (int i = lane; i < seg_words; i += 32) {
+                    const uint32_t lo = load_word_guarded(src_al + 4 * i, in_end);
+                    const uint32_t hi = lead != 0 ? load_word_guarded(src_al + 4 * i + 4, in_end) : 0u;
+                    dst4[i] = __funnelshift_r(lo, hi, 8 * lead);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- horizontal taps: lane = staged row, warp = output column (w, w+8, ...)
+        if (r0 + lane < rows) {
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(stage + lane * g.stage_stride);
+            uint8_t* hrow = hbuf + (r0 + lane) * kHbufStride;
+            for (int ox = warp; ox < bw; ox += 8) {
+                const int boff = (bh[2 * ox] - x_lo) * 3, n = bh[2 * ox + 1];   // warp-uniform
+                const int sh = (boff & 3) * 8;
+                const uint32_t* wp = row + (boff >> 2);
+                const int4* kp = reinterpret_cast<const int4*>(kh + ox * g.ksh4);
+                int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+                for (int x4 = 0; x4 < n; x4 += 4) {
+                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+                    wp += 3;
+                    const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh),
+                                   v2 = __funnelshift_r(w2, w3, sh);
+                    const int4 k = *kp++;   // taps beyond n are zero
+                    s0 += byte_of<0>(v0) * k.x; s1 += byte_of<1>(v0) * k.x; s2 += byte_of<2>(v0) * k.x;
+                    s0 += byte_of<3>(v0) * k.y; s1 += byte_of<0>(v1) * k.y; s2 += byte_of<1>(v1) * k.y;
+                    s0 += byte_of<2>(v1) * k.z; s1 += byte_of<3>(v1) * k.z; s2 += byte_of<0>(v2) * k.z;
+                    s0 += byte_of<1>(v2) * k.w; s1 += byte_of<2>(v2) * k.w; s2 += byte_of<3>(v2) * k.w;
+                }
+                hrow[ox * 3 + 0] = clip8(s0 >> 22);
+                hrow[ox * 3 + 1] = clip8(s1 >> 22);
+                hrow[ox * 3 + 2] = clip8(s2 >> 22);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- vertical taps: one word = 4 interleaved bytes of a horizontal-pass row per thread; results parked as bytes
+    uint32_t* obuf = reinterpret_cast<uint32_t*>(stage);   // [BH][48] words
+    constexpr int kRowWords = 48;                          // 64 pixels x 3 bytes
+    for (int item = tid; item < bhh * kRowWords; item += 256) {
+        const int oy = item / kRowWords, wi = item - oy * kRowWords;
+        const int ymin = bv[2 * oy] - y_lo, n = bv[2 * oy + 1];
+        const int* k = kv + oy * g.ksv;
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(hbuf + ymin * kHbufStride) + wi;
+        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21, a3 = 1 << 21;
+        for (int y = 0; y < n; ++y) {
+            const uint32_t w = p[y * (kHbufStride / 4)];
+            const int kk = k[y];
+            a0 += byte_of<0>(w) * kk;
+            a1 += byte_of<1>(w) * kk;
+            a2 += byte_of<2>(w) * kk;
+            a3 += byte_of<3>(w) * kk;
+        }
+        obuf[item] = static_cast<uint32_t>(clip8(a0 >> 22)) | (static_cast<uint32_t>(clip8(a1 >> 22)) << 8) |
+                     (static_cast<uint32_t>(clip8(a2 >> 22)) << 16) | (static_cast<uint32_t>(clip8(a3 >> 22)) << 24);
+    }
+    __syncthreads();
+    // ---- crop + LUT + planar store: lane = output column of one colour plane
+    const uint8_t* ob = reinterpret_cast<const uint8_t*>(obuf);
+    constexpr int per_row = 3 * kFusedBW;   // a multiple of 32: a warp stays inside one (row, plane)
+    // S is a multiple of both block sizes in every geometry the reference produces (448): the block lies in one tile
+    const bool one_tile = (g.S % kFusedBW == 0) && (g.S % g.BH == 0);
+    const int tile0 = (gy0 / g.S) * g.gi + (gx0 / g.S), ty0 = gy0 % g.S, tx0 = gx0 % g.S;
+    for (int idx = tid; idx < bhh * per_row; idx += 256) {
+        const int oy = idx / per_row;
+        const int rem = idx - oy * per_row;
+        const int c = rem / kFusedBW, xo = rem - c * kFusedBW;
+        if (xo >= bw) continue;
+        const int v = ob[oy * (kRowWords * 4) + xo * 3 + c];
+        int tile = tile0, y = ty0 + oy, x = tx0 + xo;
+        if (!one_tile) {
+            const int gx = gx0 + xo, gy = gy0 + oy;
+            tile = (gy / g.S) * g.gi + (gx / g.S);
+            y = gy % g.S;
+            x = gx % g.S;
+        }
+        out[(((f * g.tiles_per_frame + g.tile_offset + tile) * 3 + c) * g.S + y) * g.S + x] = cvt_out<TOut>(lut[c * 256 + v]);
+    }
+}
+
+// Block geometry of the fused kernel for one resize; false when no block height fits in shared memory (the caller then
+// falls back to the two passes).
+bool plan_fused(int F, int H, int W, int OW, int OH, int S, int gi, int tpf, int tile_offset, const DeviceCoeffs& ch,
+                const DeviceCoeffs& cv, FusedGeom* out_g, size_t* out_smem, long long* out_ctas) {
+    constexpr size_t kMaxSmem = 200 * 1024;
+    for (int BH = 32; BH >= 8; BH >>= 1) {
+        FusedGeom g;
+        g.F = F; g.H = H; g.W = W; g.OW = OW; g.OH = OH; g.S = S; g.gi = gi; g.tiles_per_frame = tpf; g.tile_offset = tile_offset;
+        g.BW = kFusedBW; g.BH = BH; g.ksh = ch.ksize; g.ksh4 = (ch.ksize + 3) & ~3; g.ksv = cv.ksize;
+        g.bounds_h = ch.bounds; g.kk_h = ch.kk; g.bounds_v = cv.bounds; g.kk_v = cv.kk;
+        g.in_bytes = (long long)F * H * W * 3;
+        const int seg = ch.max_span(g.BW) * 3 + 24;                // + rounding to whole words and the 4-word read-ahead
+        g.stage_stride = ((seg + 127) / 128) * 128 + 4;
+        g.stage_bytes = std::max(32 * g.stage_stride, BH * 3 * g.BW);
+        g.rmax = cv.max_span(BH);
+        const size_t smem = 3072 + 4 * (size_t)(g.BW * g.ksh4 + BH * g.ksv + 2 * g.BW + 2 * BH) +
+                            (((size_t)g.rmax * kHbufStride + 15) & ~(size_t)15) + (size_t)g.stage_bytes;
+        const long long ctas = (long long)F * ((OW + g.BW - 1) / g.BW) * ((OH + BH - 1) / BH);
+        if (smem > kMaxSmem || ctas <= 0 || ctas >= (1LL << 31)) continue;
+        *out_g = g;
+        *out_smem = smem;
+        *out_ctas = ctas;
+        return true;
+    }
+    return false;
+}
+
+template <typename TOut>
+int run_fused(const uint8_t* frames, TOut* out, const FusedGeom& g, size_t smem, long long ctas, const NormLut& lut,
+              cudaStream_t st) {
+    static PerDeviceOnce attr;
+    if (attr.first())
+        MJV_CUDA_OK(cudaFuncSetAttribute(resample_fused_kernel<TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    resample_fused_kernel<TOut><<<(unsigned)ctas, 256, smem, st>>>(frames, out, g, lut);
+    MJV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // grid choice of dynamic_preprocess (data.py:66-99), float64 like the reference
 void choose_grid(int width, int height, int min_num, int max_num, int image_size, int* gi, int* gj) {
     const double aspect = static_cast<double>(width) / height;
@@ -309,31 +544,36 @@ int preprocess_t(const uint8_t* frames, int F, int H, int W, int image_size, int
         return 0;
     }
     const int OW = S * gi, OH = S * gj;
-    const size_t need = static_cast<size_t>(F) * H * (OW > S ? OW : S) * 3;
-    MJV_CHECK(scratch != nullptr && scratch_bytes >= need, MJV_ERR_NOMEM,
-              "preprocess: scratch of %zu bytes needed, %zu given", need, scratch_bytes);
-    DeviceCoeffs ch, cv;
-    MJV_PROPAGATE(get_device_coeffs(W, OW, st, &ch));
-    MJV_PROPAGATE(get_device_coeffs(H, OH, st, &cv));
-    {
-        LaunchScope scope(TAG_FRAMES, st, (double)F * (3.0 * H * W + 6.0 * H * OW + 3.0 * OW * OH * sizeof(TOut)), 2);
-        resample_h_kernel<<<grid, 256, 0, st>>>(frames, scratch, F, H, W, OW, ch.bounds, ch.kk, ch.ksize);
-        resample_v_tiles_kernel<TOut><<<grid, 256, 0, st>>>(scratch, out, F, H, OW, OH, S, gi, tpf, 0, cv.bounds, cv.kk,
-                                                            cv.ksize, lut);
-    }
-    MJV_CUDA_OK(cudaGetLastError());
-    if (tpf > blocks) {  // thumbnail: whole frame -> S x S (data.py:114-116)
-        DeviceCoeffs th, tv;
-        MJV_PROPAGATE(get_device_coeffs(W, S, st, &th));
-        MJV_PROPAGATE(get_device_coeffs(H, S, st, &tv));
+    // MJV_RESIZE_TWO_PASS=1 forces the older two-kernel path (tools / A-B measurements; also the fallback for geometries whose
+    // block does not fit in shared memory - it needs the caller's scratch for the [F,H,OW,3] intermediate)
+    const char* two = getenv("MJV_RESIZE_TWO_PASS");
+    const bool allow_fused = !(two != nullptr && two[0] == '1');
+    const auto resize = [&](int ow, int oh, int grid_i, int tile_offset) -> int {
+        DeviceCoeffs ch, cv;
+        MJV_PROPAGATE(get_device_coeffs(W, ow, st, &ch));
+        MJV_PROPAGATE(get_device_coeffs(H, oh, st, &cv));
+        FusedGeom fg;
+        size_t fsmem = 0;
+        long long fctas = 0;
+        if (allow_fused && plan_fused(F, H, W, ow, oh, S, grid_i, tpf, tile_offset, ch, cv, &fg, &fsmem, &fctas)) {
+            // algorithmic bytes: the frame read once, the tiles written once
+            LaunchScope scope(TAG_FRAMES, st, (double)F * (3.0 * H * W + 3.0 * ow * oh * sizeof(TOut)), 1);
+            return run_fused<TOut>(frames, out, fg, fsmem, fctas, lut, st);
+        }
+        const size_t need = static_cast<size_t>(F) * H * ow * 3;
+        MJV_CHECK(scratch != nullptr && scratch_bytes >= need, MJV_ERR_NOMEM,
+                  "preprocess: scratch of %zu bytes needed, %zu given", need, scratch_bytes);
         {
-            LaunchScope scope(TAG_FRAMES, st, (double)F * (3.0 * H * W + 6.0 * H * S + 3.0 * S * S * sizeof(TOut)), 2);
-            resample_h_kernel<<<grid, 256, 0, st>>>(frames, scratch, F, H, W, S, th.bounds, th.kk, th.ksize);
-            resample_v_tiles_kernel<TOut><<<grid, 256, 0, st>>>(scratch, out, F, H, S, S, S, 1, tpf, blocks, tv.bounds,
-                                                                tv.kk, tv.ksize, lut);
+            LaunchScope scope(TAG_FRAMES, st, (double)F * (3.0 * H * W + 6.0 * H * ow + 3.0 * ow * oh * sizeof(TOut)), 2);
+            resample_h_kernel<<<grid, 256, 0, st>>>(frames, scratch, F, H, W, ow, ch.bounds, ch.kk, ch.ksize);
+            resample_v_tiles_kernel<TOut><<<grid, 256, 0, st>>>(scratch, out, F, H, ow, oh, S, grid_i, tpf, tile_offset, cv.bounds,
+                                                                cv.kk, cv.ksize, lut);
         }
         MJV_CUDA_OK(cudaGetLastError());
-    }
+        return 0;
+    };
+    MJV_PROPAGATE(resize(OW, OH, gi, 0));
+    if (tpf > blocks) MJV_PROPAGATE(resize(S, S, 1, blocks));  // thumbnail: whole frame -> S x S (data.py:114-116)
     return 0;
 }
 

@@ -71,3 +71,23 @@ def test_load_video_from_a_real_file(built_lib, tmp_path):
     ref_pv, ref_counts = port.load_video_frames(decoded, num_segments=4, max_num=6, fps=rd.get_avg_fps())
     assert counts == ref_counts and pv.shape == ref_pv.shape and pv.dtype == torch.float32 and pv.device.type == "cpu"
     assert torch.equal(pv, ref_pv)
+
+
+@pytest.mark.parametrize("H,W,max_num", [(720, 1280, 1), (720, 1280, 6), (1080, 1920, 1), (2160, 3840, 1), (77, 100, 1),
+                                         (449, 447, 2), (448, 1344, 6), (1344, 448, 6), (333, 1001, 12)])
+def test_fused_resize_equals_two_pass(built_lib, monkeypatch, H, W, max_num):
+    """The fused resize kernel (horizontal taps into shared memory, vertical taps + crop + LUT in the same CTA) writes the
+    same bits as the two-kernel path through Pillow's uint8 intermediate image, thumbnails included; odd widths exercise
+    the unaligned row starts, 4K frames the smaller block heights."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from mj_video_b200.data_processor import preprocess_frames
+    g = torch.Generator(device="cuda").manual_seed(H * 7 + W)
+    frames = torch.randint(0, 256, (3, H, W, 3), dtype=torch.uint8, device="cuda", generator=g)
+    monkeypatch.delenv("MJV_RESIZE_TWO_PASS", raising=False)
+    fused, tpf = preprocess_frames(frames, 448, max_num, True, torch.float32)
+    fused16, _ = preprocess_frames(frames, 448, max_num, True, torch.bfloat16)
+    monkeypatch.setenv("MJV_RESIZE_TWO_PASS", "1")
+    two, tpf2 = preprocess_frames(frames, 448, max_num, True, torch.float32)
+    assert tpf == tpf2 and torch.equal(fused, two)
+    assert torch.equal(fused16, two.to(torch.bfloat16))

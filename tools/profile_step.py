@@ -12,7 +12,7 @@ from mj_video_b200 import ops, synth  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--kernel", default=None, choices=[None, "swiglu", "gelu", "resid_fc2", "qkv_vit", "attn_vit", "attn_llm",
-                                                   "layernorm", "rmsnorm", "gather_ln", "frames", "im2col"])
+                                                   "layernorm", "rmsnorm", "gather_ln", "frames", "im2col", "resize720"])
 ap.add_argument("--batch", type=int, default=32)
 args = ap.parse_args()
 dev = "cuda"
@@ -102,6 +102,11 @@ elif args.kernel == "gather_ln":
 elif args.kernel == "frames":
     from mj_video_b200.data_processor import preprocess_frames
     fr = torch.randint(0, 256, (256, 448, 448, 3), device=dev, dtype=torch.uint8)
+    px = torch.empty(256, 3, 448, 448, device=dev, dtype=torch.bfloat16)
+    fn = lambda: preprocess_frames(fr, 448, 1, True, torch.bfloat16, out=px)  # noqa: E731
+elif args.kernel == "resize720":   # fused bicubic resize, 256 frames 1280x720 -> 448x448
+    from mj_video_b200.data_processor import preprocess_frames
+    fr = torch.randint(0, 256, (256, 720, 1280, 3), device=dev, dtype=torch.uint8)
     px = torch.empty(256, 3, 448, 448, device=dev, dtype=torch.bfloat16)
     fn = lambda: preprocess_frames(fr, 448, 1, True, torch.bfloat16, out=px)  # noqa: E731
 elif args.kernel == "im2col":

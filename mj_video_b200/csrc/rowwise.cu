@@ -267,13 +267,13 @@ __global__ void cls_rows_kernel(const __nv_bfloat16* __restrict__ cls, const __n
     hidden[static_cast<long long>(t) * S * C + c] = __float2bfloat16_rn(__bfloat162float(cls[c]) + __bfloat162float(pos[c]));
 }
 
-// rows up to 1024 columns: one warp per row; wider rows: 2 or 4 warps per row with <= 4 chunks per thread
+// rows up to 1024 columns: one warp per row; wider rows: 2 warps per row with 4 / 6 / 8 chunks per thread
 template <bool GATHER>
 int launch_ln(const __nv_bfloat16* x, const __nv_bfloat16* w, const __nv_bfloat16* b, __nv_bfloat16* out,
               long long rows, int C, float eps, long long ldx, int grid_g, int seq, cudaStream_t st) {
     MJV_CHECK(C % 8 == 0 && C <= 4096, MJV_ERR_ARG, "layernorm: C=%d unsupported", C);
     const int nchunk = (C + 255) / 256;
-    const int wpr = nchunk <= 4 ? 1 : (nchunk <= 8 ? 2 : 4);
+    const int wpr = nchunk <= 4 ? 1 : 2;   // must match the W of the instantiation chosen below
     const int rows_per_block = kWarpsPerBlock / wpr;
     const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
     const int threads = kWarpsPerBlock * 32;
@@ -283,7 +283,8 @@ int launch_ln(const __nv_bfloat16* x, const __nv_bfloat16* w, const __nv_bfloat1
     else if (nchunk <= 2) MJV_LN(2, 1);
     else if (nchunk <= 4) MJV_LN(4, 1);
     else if (nchunk <= 8) MJV_LN(4, 2);
-    else MJV_LN(4, 4);
+    else if (nchunk <= 12) MJV_LN(6, 2);
+    else MJV_LN(8, 2);   // projector LayerNorm over 4 x 1024 columns: 8 loads in flight per lane instead of 4
 #undef MJV_LN
     MJV_CUDA_OK(cudaGetLastError());
     return 0;
@@ -315,7 +316,9 @@ int rmsnorm(const void* x, const void* w, void* out, long long rows, int C, floa
     if (rows == 0) return 0;
     MJV_CHECK(C % 8 == 0 && C <= 4096, MJV_ERR_ARG, "rmsnorm: C=%d unsupported", C);
     const int nchunk = (C + 255) / 256;
-    const int wpr = nchunk <= 4 ? 1 : (nchunk <= 8 ? 2 : 4);
+    // two warps per row up to C = 4096 with 4-8 16-byte loads in flight per lane: at C = 3072 (Phi-3 / InternVL2-4B) the
+    // four-warp split left 3 loads per lane in flight and ran at 2.47 TB/s (profiles/r01)
+    const int wpr = nchunk <= 4 ? 1 : 2;   // must match the W of the instantiation chosen below
     const int rows_per_block = kWarpsPerBlock / wpr;
     const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
     const int threads = kWarpsPerBlock * 32;
@@ -326,7 +329,8 @@ int rmsnorm(const void* x, const void* w, void* out, long long rows, int C, floa
     else if (nchunk <= 2) MJV_RMS(2, 1);
     else if (nchunk <= 4) MJV_RMS(4, 1);
     else if (nchunk <= 8) MJV_RMS(4, 2);
-    else MJV_RMS(4, 4);
+    else if (nchunk <= 12) MJV_RMS(6, 2);
+    else MJV_RMS(8, 2);
 #undef MJV_RMS
     MJV_CUDA_OK(cudaGetLastError());
     return 0;

@@ -278,7 +278,7 @@ def test_rowwise_kernels(ops, built_lib):
     lib = built_lib
     g = torch.Generator(device="cuda").manual_seed(3)
     st = _lib.current_stream()
-    for rows, Cc in [(1000, 1024), (77, 128), (300, 4096), (5, 256)]:
+    for rows, Cc in [(1000, 1024), (77, 128), (300, 4096), (5, 256), (200, 3072), (123, 2048), (64, 1536), (9, 2304)]:
         x = torch.randn(rows, Cc, device="cuda", generator=g).bfloat16()
         w = torch.randn(Cc, device="cuda", generator=g).bfloat16()
         b = torch.randn(Cc, device="cuda", generator=g).bfloat16()

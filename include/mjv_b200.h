@@ -156,8 +156,11 @@ int mjv_im2col_patches(const void* px, int32_t px_dtype, void* out, int32_t T, i
  * Frame path: uint8 [n_frames, H, W, 3] frames (device) -> normalised CHW tiles [n_frames*tiles_per_frame,3,S,S].
  * Replaces the per-frame body of load_video (data_processor/data.py:158-179): dynamic_preprocess (data.py:81-117,
  * PIL bicubic resize + row-major crops + thumbnail) and build_transform (data.py:56-64). Bit-exact with Pillow.
- * `out` NULL = query tiles_per_frame only. `scratch` (uint8, >= n_frames*H*max(S*gi,S)*3 bytes) is needed only when a
- * resize happens. mjv_choose_grid / mjv_bicubic_coeffs are pure host helpers (usable without a GPU).
+ * `out` NULL = query tiles_per_frame only. A resize runs in ONE fused kernel (horizontal taps into shared memory, vertical
+ * taps + crop + normalisation in the same CTA) and needs no scratch. `scratch` (uint8, >= n_frames*H*max(S*gi,S)*3 bytes)
+ * is used only by the two-pass fallback (a block that does not fit in shared memory, or MJV_RESIZE_TWO_PASS=1 in the
+ * environment): without it that case returns MJV_ERR_NOMEM, and the caller retries with the buffer.
+ * mjv_choose_grid / mjv_bicubic_coeffs are pure host helpers (usable without a GPU).
  * ---------------------------------------------------------------------------------------------------------- */
 int mjv_preprocess_frames(const void* frames_u8, int32_t n_frames, int32_t height, int32_t width, int32_t image_size,
                           int32_t max_num, int32_t use_thumbnail, void* out, int32_t out_dtype, void* scratch,
@@ -202,7 +205,9 @@ int mjv_create(const mjv_config* cfg, mjv_handle** out);
 void mjv_destroy(mjv_handle* h);
 /* Copy + re-pack one tensor of the reference state dict (SURVEY §A.2 key names; also "rope.cos"/"rope.sin"
  * [max_pos, head_dim/2] fp32 tables built by the host shim exactly as InternLM2RotaryEmbedding does).
- * `data` may be host or device memory. Unused keys (e.g. language_model.output.weight) are accepted and dropped. */
+ * `data` may be host or device memory. Unused keys (e.g. language_model.output.weight) are accepted and dropped.
+ * Llama-style separate q/k/v and gate/up keys, InternLM2's fused wqkv, and Phi-3's fused `self_attn.qkv_proj.weight`
+ * (rows q|k|v) / `mlp.gate_up_proj.weight` (rows gate|up) are all accepted. */
 int mjv_load_weight(mjv_handle* h, const char* key, const void* data, const int64_t* shape, int32_t ndim,
                     int32_t dtype);
 /* Check that every tensor the forward needs is present; returns MJV_ERR_STATE and names the first missing key. */

@@ -14,6 +14,9 @@ MJV_DTYPE_F32, MJV_DTYPE_BF16, MJV_DTYPE_F16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_RESID, EPI_SWIGLU, EPI_QKV_LLM, EPI_QKV_VIT, EPI_PATCH, EPI_SCATTER = range(8)
 
 
+MJV_ERR_NOMEM = -5   # include/mjv_b200.h
+
+
 class MjvError(RuntimeError):
     pass
 

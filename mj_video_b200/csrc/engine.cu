@@ -195,7 +195,7 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
         rows = 1;
     }
     if (ends_with(key, "language_model.output.weight")) return 0;  // LM head: never used by the reward path
-    // Phi-3 checkpoints (InternVL2-4B, /root/reference/README.md:18) ship q|k|v and gate|up as single matrices
+    // Phi-3 checkpoints (InternVL2-4B; reference README.md:18) ship q|k|v and gate|up as single matrices
     // (transformers Phi3Attention.qkv_proj: rows [q heads | k heads | v heads]; Phi3MLP.gate_up_proj: rows [gate | up], chunk(2)).
     // Row ranges of a row-major matrix are contiguous: hand them on under the separate Llama-style names.
     {

@@ -220,14 +220,16 @@ def preprocess_frames(frames_u8: torch.Tensor, input_size=448, max_num=1, use_th
             out = torch.empty((F * tpf.value, 3, input_size, input_size), dtype=dtype, device=frames_u8.device)
         elif out.numel() != F * tpf.value * 3 * input_size * input_size or out.dtype != dtype or not out.is_contiguous():
             raise ValueError("preprocess_frames: `out` has the wrong size / dtype")
-        gi, gj = find_closest_aspect_ratio(W, H, 1, max_num, input_size)
-        scratch = None
-        if not (gi * gj == 1 and H == input_size and W == input_size):
-            scratch = torch.empty(F * H * max(input_size * gi, input_size) * 3, dtype=torch.uint8,
-                                  device=frames_u8.device)
-        _lib.check(lib.mjv_preprocess_frames(frames_u8.data_ptr(), F, H, W, input_size, max_num, int(use_thumbnail),
-                                             out.data_ptr(), out_dt, _lib.ptr(scratch),
-                                             0 if scratch is None else scratch.numel(), C.byref(tpf), st))
+        # the fused resize kernel needs no scratch; only the two-pass fallback (a block that does not fit in shared memory,
+        # or MJV_RESIZE_TWO_PASS=1) asks for the uint8 [F,H,OW,3] intermediate, by returning MJV_ERR_NOMEM
+        rc = lib.mjv_preprocess_frames(frames_u8.data_ptr(), F, H, W, input_size, max_num, int(use_thumbnail),
+                                       out.data_ptr(), out_dt, None, 0, C.byref(tpf), st)
+        if rc == _lib.MJV_ERR_NOMEM:
+            gi, gj = find_closest_aspect_ratio(W, H, 1, max_num, input_size)
+            scratch = torch.empty(F * H * max(input_size * gi, input_size) * 3, dtype=torch.uint8, device=frames_u8.device)
+            rc = lib.mjv_preprocess_frames(frames_u8.data_ptr(), F, H, W, input_size, max_num, int(use_thumbnail),
+                                           out.data_ptr(), out_dt, scratch.data_ptr(), scratch.numel(), C.byref(tpf), st)
+        _lib.check(rc)
     return out, tpf.value
 
 

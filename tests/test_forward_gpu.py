@@ -269,6 +269,28 @@ def test_full_size_large_batch_rows_are_independent(full_engine, gpu):
     assert (small - big[:4]).abs().max().item() <= 2e-3, (small - big[:4]).abs().max().item()
 
 
+def test_full_size_2b_multi_tile_row_vs_oracle(full_engine, gpu):
+    """BASELINE configs[3] geometry at FULL model size: 6 frames of 896x1344 -> max_num=6 -> 7 tiles per frame (fused resize
+    kernel + thumbnail), 42 tiles and ~10.9k tokens in one row (86 query blocks per head, long causal items), together with
+    a short single-tile row in the same batch, against the oracle in bf16 on the GPU."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from oracle import port
+    d, sd, eng = full_engine
+    vid = synth.make_video(91, n_frames=12, height=896, width=1344)
+    pv_long, counts = load_video(vid, num_segments=6, max_num=6, device="cuda", dtype=torch.bfloat16)
+    assert counts == [7] * 6 and pv_long.shape[0] == 42
+    pv_short, c2 = load_video(synth.make_video(92), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)
+    pv = torch.cat([pv_long, pv_short])
+    ids, mask = synth.pad_batch([synth.make_input_ids(3, counts, n_cap=60), synth.make_input_ids(4, c2, n_cap=25)])
+    assert ids.shape[1] > 10800
+    mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
+    o16 = port.Oracle(d, sd, dtype=torch.bfloat16, device=gpu).forward(pv, ids, mask)
+    _check(mine, o16)
+    del o16
+    torch.cuda.empty_cache()
+
+
 def test_long_visual_sequence_config4_shapes(tiny_engine, gpu):
     """BASELINE configs[3] shapes on the small model: 16 frames of 896x1344 -> dynamic_preprocess max_num=6 -> 7 tiles per
     frame = 112 tiles, N = 28 8xx tokens in ONE row (resize kernels, 226 query blocks, RoPE positions up to ~29k)."""
@@ -353,6 +375,28 @@ def test_config5_widths_vs_oracle(gpu):
     _check(mine, o16)
     o32 = port.Oracle(d, sd, dtype=torch.float32, device=gpu, inv_freq_dtype=torch.bfloat16).forward(pv.float(), ids, mask)
     _check(mine, o32)
+
+
+def test_config5_full_depth_row_vs_oracle(gpu):
+    """BASELINE configs[4] at its FULL depth (24 ViT + 32 LLM layers, d 3072, 32 heads x 96, ~3.8 B parameters): one row of
+    8 frames against the oracle in bf16 on the GPU (the cut-depth test above adds the fp32 comparison)."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from mj_video_b200.engine import Engine, EngineDims
+    from oracle import port
+    d = synth.dims_4b()
+    sd = synth.make_state_dict(d, seed=78, include_lm_head=False)
+    eng = Engine(EngineDims.from_synth(d), gpu)
+    eng.load_state_dict(sd)
+    pv = load_video(synth.make_video(310), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)[0]
+    ids, mask = synth.pad_batch([synth.make_input_ids(2, [1] * 8, n_cap=44)])
+    mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
+    del eng
+    torch.cuda.empty_cache()
+    o16 = port.Oracle(d, sd, dtype=torch.bfloat16, device=gpu).forward(pv, ids, mask)
+    _check(mine, o16)
+    del o16
+    torch.cuda.empty_cache()
 
 
 def test_pair_scorer_matches_direct_forward(tiny_engine, gpu):

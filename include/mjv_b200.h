@@ -90,6 +90,10 @@ typedef struct mjv_gemm_desc {
     int32_t cta_group;    /* 0 = auto (CTA pairs when block_n = 256), 1 or 2         */
     int32_t v_head_dim;   /* QKV_LLM: columns per V head in the N layout and rows per V^T plane (0 = 128); a multiple of
                              32 — V needs no rotary slot, so narrow heads (e.g. 96) are packed                          */
+    int32_t qk_head_slot; /* QKV_LLM: columns per q / k head in N. 0 or 128: rotate-half pairs sit 64 columns apart inside a
+                             128-wide slot. 96: native head_dim-96 layout, the pair (d, d+48) is stored in ADJACENT columns
+                             (2d, 2d+1) - q.k is invariant under the common permutation - so RoPE works chunk by chunk and
+                             a head never has to align with the 128/256-column tile                                   */
 } mjv_gemm_desc;
 
 int mjv_gemm_bf16(const mjv_gemm_desc* desc, void* stream);
@@ -128,6 +132,10 @@ typedef struct mjv_attn_desc {
      *   v_head_dim   rows per V^T plane (0 = head_dim); rows beyond it are zero-filled by TMA,
      *   out_head_dim columns per head written to `out` (0 = head_dim; a multiple of 32), head h at column h*out_head_dim. */
     int32_t v_head_dim, out_head_dim;
+    /* qk_head_stride: columns from one q (or k) head to the next in their tensors (0 = head_dim). With 96 and head_dim 128
+     * the 128-wide tile is loaded from column h*96 and only the first 96 columns enter Q.K^T (6 of the 8 k-steps): the
+     * remaining columns (the next head, or TMA zero fill past the last one) are never read by the MMA. Varlen causal only. */
+    int32_t qk_head_stride;
 } mjv_attn_desc;
 
 int mjv_attention(const mjv_attn_desc* desc, void* stream);

@@ -33,7 +33,7 @@ class GemmDesc(C.Structure):
         ("row_pos", C.c_void_p), ("row_map", C.c_void_p), ("row_vt", C.c_void_p), ("pos_emb", C.c_void_p),
         ("n_q_cols", C.c_int32), ("n_k_cols", C.c_int32),
         ("vt_stride_head", C.c_int64), ("vt_ld", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32),
-        ("cta_group", C.c_int32), ("v_head_dim", C.c_int32),
+        ("cta_group", C.c_int32), ("v_head_dim", C.c_int32), ("qk_head_slot", C.c_int32),
     ]
 
 
@@ -47,7 +47,7 @@ class AttnDesc(C.Structure):
         ("nseq", C.c_int32), ("seq_len", C.c_int32),
         ("cu_seqlens", C.c_void_p), ("work", C.c_void_p), ("vt_starts", C.c_void_p), ("vt_cols", C.c_int64),
         ("n_work", C.c_int32), ("scale", C.c_float), ("flops_hint", C.c_double),
-        ("v_head_dim", C.c_int32), ("out_head_dim", C.c_int32),
+        ("v_head_dim", C.c_int32), ("out_head_dim", C.c_int32), ("qk_head_stride", C.c_int32),
     ]
 
 

@@ -424,7 +424,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         const uint32_t qaddr = ptx::smem_u32(sQ) + buf * L::kQBytes + (r >> 3) * 1024 + (r & 7) * 128;
                         const uint4* kt = reinterpret_cast<const uint4*>(
                             args.k_ptr + static_cast<long long>(t.row_base + len - 1) * args.ldk + args.k_col0 +
-                            (t.kvh + (t.dual ? tt : 0)) * HD);
+                            (t.kvh + (t.dual ? tt : 0)) * args.qk_stride);
                         float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
@@ -763,7 +763,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
                         for (int kd = 0; kd < HD / 64; ++kd)
                             ptx::tma_load_3d(sQ + buf * L::kQBytes + kd * (BQ * 128), &tmQ, &q_full[buf],
-                                             args.q_col0 + t.h[tt] * HD + kd * 64, t.tma_row0 + t.q0[tt], t.tma_batch,
+                                             args.q_col0 + t.h[tt] * args.qk_stride + kd * 64, t.tma_row0 + t.q0[tt], t.tma_batch,
                                              ptx::kEvictFirst);
                         ++n_use[tt];
                     }
@@ -776,7 +776,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
                             for (int kd = 0; kd < HD / 64; ++kd)
                                 ptx::tma_load_3d(sK + kst * L::kKBytes + kd * (BKV * 128), &tmK, &k_full[kst],
-                                                 args.k_col0 + (t.kvh + s) * HD + kd * 64, t.tma_row0 + j * BKV, t.tma_batch,
+                                                 args.k_col0 + (t.kvh + s) * args.qk_stride + kd * 64, t.tma_row0 + j * BKV, t.tma_batch,
                                                  ptx::kEvictLast);
                             if (++kst == KS) { kst = 0; kph ^= 1; }
                             if constexpr (KS == 1) {
@@ -786,7 +786,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                 if (j + 1 < t.nblk_max && !t.dual) {
 #pragma unroll
                                     for (int kd = 0; kd < HD / 64; ++kd)
-                                        ptx::tma_prefetch_3d(&tmK, args.k_col0 + t.kvh * HD + kd * 64,
+                                        ptx::tma_prefetch_3d(&tmK, args.k_col0 + t.kvh * args.qk_stride + kd * 64,
                                                              t.tma_row0 + (j + 1) * BKV, t.tma_batch);
                                 }
                             }
@@ -888,6 +888,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
             const uint64_t q_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sQ));
             const uint64_t k_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sK));
+            const int qk_ksteps = args.qk_ksteps;
             int kst = 0;
             uint32_t kph = 0;
             uint32_t q_use[2] = {0, 0};
@@ -922,9 +923,12 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         if (leader) {
 #pragma unroll
                             for (int ks = 0; ks < HD / 16; ++ks) {
-                                const uint64_t a = a0 + static_cast<uint64_t>(((ks >> 2) * (BQ * 128) + (ks & 3) * 32) >> 4);
-                                const uint64_t b = b0 + static_cast<uint64_t>(((ks >> 2) * (BKV * 128) + (ks & 3) * 32) >> 4);
-                                ptx::mma_bf16_ss(d, a, b, idesc_s, ks != 0 ? 1u : 0u);
+                                // packed head_dim-96 heads: columns 96..127 of the tile belong to the next head, not read
+                                if (ks < qk_ksteps) {
+                                    const uint64_t a = a0 + static_cast<uint64_t>(((ks >> 2) * (BQ * 128) + (ks & 3) * 32) >> 4);
+                                    const uint64_t b = b0 + static_cast<uint64_t>(((ks >> 2) * (BKV * 128) + (ks & 3) * 32) >> 4);
+                                    ptx::mma_bf16_ss(d, a, b, idesc_s, ks != 0 ? 1u : 0u);
+                                }
                             }
                             ptx::mma_commit(&s_full[tt * kNSB + sel2(tt, t_slot)]);
                             if (last_of_block) ptx::mma_commit(&k_empty[kst]);  // K tile free once the S MMAs of both tiles retire

@@ -66,13 +66,16 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     const int out_hd = d.out_head_dim > 0 ? d.out_head_dim : hd;
     MJV_CHECK(v_hd <= hd && out_hd <= hd && out_hd % 32 == 0, MJV_ERR_ARG,
               "attention: v_head_dim %d / out_head_dim %d must fit the %d-wide tile (out a multiple of 32)", v_hd, out_hd, hd);
+    const int qk_stride = d.qk_head_stride > 0 ? d.qk_head_stride : hd;
+    MJV_CHECK(qk_stride == hd || (impl == 2 && varlen && hd == 128 && qk_stride == 96), MJV_ERR_ARG,
+              "attention: qk_head_stride %d unsupported (head_dim, or 96 under the 128-wide causal varlen tile)", qk_stride);
     CUtensorMap tq, tk, tv;
     if (varlen) {
-        uint64_t qd[3] = {(uint64_t)(d.q_col0 + d.heads * hd), (uint64_t)d.total_rows, 1};
+        uint64_t qd[3] = {(uint64_t)(d.q_col0 + d.heads * qk_stride), (uint64_t)d.total_rows, 1};
         uint64_t qs[3] = {1, (uint64_t)d.ldq, (uint64_t)d.ldq * (uint64_t)d.total_rows};
         uint32_t qb[3] = {64, 128, 1};
         MJV_PROPAGATE(make_tmap_bf16(&tq, d.q, 3, qd, qs, qb));
-        uint64_t kd[3] = {(uint64_t)(d.k_col0 + d.kv_heads * hd), (uint64_t)d.total_rows, 1};
+        uint64_t kd[3] = {(uint64_t)(d.k_col0 + d.kv_heads * qk_stride), (uint64_t)d.total_rows, 1};
         uint64_t ks[3] = {1, (uint64_t)d.ldk, (uint64_t)d.ldk * (uint64_t)d.total_rows};
         uint32_t kb[3] = {64, (uint32_t)bkv, 1};
         MJV_PROPAGATE(make_tmap_bf16(&tk, d.k, 3, kd, ks, kb));
@@ -112,6 +115,8 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     a.scale_log2 = d.scale * 1.4426950408889634f;
     a.batched = varlen ? 0 : 1;
     a.out_hd = out_hd;
+    a.qk_stride = qk_stride;
+    a.qk_ksteps = qk_stride / 16;
 
     // algorithmic FLOPs: 4*heads*hd*S^2 per sequence (bidirectional); causal work is supplied by the caller (flops_hint)
     double work = d.flops_hint;

@@ -45,6 +45,9 @@ struct AttnArgs {
     int pair_heads;         // attention2 (attn2_sm100.cuh), varlen: the two query tiles of an item are the heads 2p, 2p+1
     int pair_tail;          // attention2, batched, odd q-block count (ViT: 1025 = 8 x 128 + 1): the last q-blocks of heads 2p, 2p+1
                             // share an item (each tile with its OWN K/V stream) instead of running as two one-tile items
+    int qk_stride;          // attention2: columns from one q / k head to the next in their tensors (= HD, or 96 for packed
+                            // head_dim-96 heads under the 128-wide tile)
+    int qk_ksteps;          // attention2: 16-column k-steps of Q.K^T that hold real columns (HD / 16, or 6 of 8 for head_dim 96)
     int kv_tail;            // attention2, batched bidirectional head_dim 64, seq_len % 128 == 1 (ViT: 1025): the last key is folded
                             // in on the CUDA cores (softmax warps: q.k_last; epilogue: + p_last * v_last) instead of costing
                             // every item a ninth 128-column step with one valid column

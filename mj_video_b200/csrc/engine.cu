@@ -113,14 +113,25 @@ size_t dtype_size(int dt) { return dt == MJV_DTYPE_F32 ? 4 : 2; }
 // every pad column comes from an all-zero weight row, i.e. is exactly 0 in q, k, v and the attention output. The
 // permutation is applied to q and k alike, so q.k is unchanged; `wo` gets matching zero columns.
 constexpr int kHeadSlot = 128;
-inline int qk_slot_dim(int d, int hd) { return d < hd / 2 ? d : 64 + (d - hd / 2); }
+// head_dim 96 (Phi-3-mini shapes, BASELINE configs[4]) gets a NATIVE 96-wide slot when the q and k column counts stay
+// multiples of the 128-column epilogue group (heads and kv heads multiples of 4): the rotary pair (d, d + 48) is stored in
+// adjacent columns (2d, 2d + 1), the QKV GEMM has no pad columns (N 11264 -> 9216 at 32 + 32 + 32 heads) and attention
+// feeds only 6 of the 8 k-steps of its 128-wide Q / K tiles to the tensor core (mjv_attn_desc.qk_head_stride).
+inline int qk_head_slot(const mjv_config& c) {
+    const int hd = c.llm_hidden / c.llm_heads;
+    return (hd == 96 && c.llm_heads % 4 == 0 && c.llm_kv_heads % 4 == 0) ? 96 : kHeadSlot;
+}
+inline int qk_slot_dim(int d, int hd, int hs) {
+    if (hs == 96) return d < hd / 2 ? 2 * d : 2 * (d - hd / 2) + 1;
+    return d < hd / 2 ? d : 64 + (d - hd / 2);
+}
 // V needs no rotary slot and the attention output no padding: when head_dim is a multiple of 32 (e.g. 96) V heads are
 // packed in the QKV GEMM's N (if the total stays a multiple of the 128-column tile) and the attention kernel writes only
 // head_dim columns per head, so `wo` keeps its original K.
 inline int v_head_width(const mjv_config& c) {
     const int hd = c.llm_hidden / c.llm_heads;
     if (hd % 32 != 0) return kHeadSlot;
-    const long long qk = static_cast<long long>(c.llm_heads + c.llm_kv_heads) * kHeadSlot;
+    const long long qk = static_cast<long long>(c.llm_heads + c.llm_kv_heads) * qk_head_slot(c);
     const long long packed = qk + static_cast<long long>(c.llm_kv_heads) * hd;
     const long long padded = qk + static_cast<long long>(c.llm_kv_heads) * kHeadSlot;
     // keep the 256-column CTA-pair tile whenever the padded layout would have it
@@ -244,7 +255,7 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
     }
 
     const int hd = c.llm_hidden / c.llm_heads;
-    const int hs = kHeadSlot;
+    const int hs = qk_head_slot(c);
     const int hv = v_head_width(c), ho = o_head_width(c);
     const long long v_base = static_cast<long long>(c.llm_heads + c.llm_kv_heads) * hs;  // first V row of the fused weight
     const long long qkv_rows = v_base + static_cast<long long>(c.llm_kv_heads) * hv;
@@ -265,8 +276,8 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
                 for (int d = 0; d < hd; ++d) {
                     const int src = (kv * (g + 2) + s) * hd + d;
                     int dst;
-                    if (s < g) dst = (kv * g + s) * hs + qk_slot_dim(d, hd);
-                    else if (s == g) dst = (c.llm_heads + kv) * hs + qk_slot_dim(d, hd);
+                    if (s < g) dst = (kv * g + s) * hs + qk_slot_dim(d, hd, hs);
+                    else if (s == g) dst = (c.llm_heads + kv) * hs + qk_slot_dim(d, hd, hs);
                     else dst = static_cast<int>(v_base) + kv * hv + d;
                     row_map[src] = dst;
                 }
@@ -281,7 +292,7 @@ int load_weight(mjv_handle* h, const char* key_c, const void* data, const int64_
         row_map.resize(rows);
         for (long long r = 0; r < rows; ++r) {
             const int head = static_cast<int>(r / hd), d = static_cast<int>(r % hd);
-            row_map[r] = which == 'v' ? static_cast<int>(v_base) + head * hv + d : (base + head) * hs + qk_slot_dim(d, hd);
+            row_map[r] = which == 'v' ? static_cast<int>(v_base) + head * hv + d : (base + head) * hs + qk_slot_dim(d, hd, hs);
         }
     } else if (ends_with(key, "attention.wo.weight")) {
         MJV_CHECK(cols == static_cast<long long>(c.llm_heads) * hd, MJV_ERR_ARG, "%s: unexpected cols %lld", key.c_str(), cols);
@@ -444,7 +455,7 @@ Dims dims_of(const mjv_handle* h) {
     d.Hq = c.llm_heads;
     d.Hkv = c.llm_kv_heads;
     d.hd = c.llm_hidden / c.llm_heads;
-    d.hs = kHeadSlot;
+    d.hs = qk_head_slot(c);
     d.hv = v_head_width(c);
     d.ho = o_head_width(c);
     return d;
@@ -625,7 +636,7 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
     MJV_CHECK(M > 0 && M < (1LL << 31) / 16, MJV_ERR_ARG, "bad token count %lld", M);
     MJV_CHECK(b.max_seq_len > 0 && b.max_seq_len <= h->rope_rows, MJV_ERR_ARG,
               "longest sequence (%d tokens) exceeds the loaded RoPE table (%lld rows)", b.max_seq_len, h->rope_rows);
-    const int nq = d.Hq * d.hs, nk = d.Hkv * d.hs;   // q / k columns (128-wide rotary slots)
+    const int nq = d.Hq * d.hs, nk = d.Hkv * d.hs;   // q / k columns (128-wide rotary slots, or native 96)
     const int nv = d.Hkv * d.hv;                      // V columns of the QKV GEMM (packed heads)
     const int no = d.Hq * d.ho;                       // attention output columns = K of `wo`
     __nv_bfloat16* hcur = static_cast<__nv_bfloat16*>(embeds);
@@ -654,6 +665,7 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
         {
             mjv_gemm_desc g = gemm_base(xn, d.D, w.wqkv, d.D, q, nq, (int)M, nq + nk + nv, d.D, MJV_EPI_QKV_LLM);
             g.v_head_dim = d.hv;
+            g.qk_head_slot = d.hs;
             g.out_k = k;
             g.out_vt = vt;
             g.rope_cos = h->rope_cos;
@@ -681,7 +693,8 @@ int llm_prefill(mjv_handle* h, void* embeds, const mjv_batch& b, void* gathered,
             a.vt_ld = b.vt_cols;
             a.vt_plane_stride = static_cast<long long>(d.hv) * b.vt_cols;
             a.total_rows = M;
-            a.head_dim = d.hs;
+            a.head_dim = kHeadSlot;          // the kernel's tile width
+            a.qk_head_stride = d.hs;         // 128, or 96: heads packed, 6 of 8 k-steps
             a.heads = d.Hq;
             a.kv_heads = d.Hkv;
             a.causal = 1;

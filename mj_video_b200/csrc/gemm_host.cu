@@ -124,6 +124,7 @@ int gemm_bf16(const mjv_gemm_desc& d, cudaStream_t stream) {
     a.seq = d.seq;
     a.heads = d.heads;
     a.v_hd = d.v_head_dim > 0 ? d.v_head_dim : 128;
+    a.qk_slot = d.qk_head_slot > 0 ? d.qk_head_slot : 128;
 
     // output tensor maps for the TMA-store epilogue (BN == 256): [32 rows x 64 columns] boxes, 128B swizzle
     CUtensorMap tmO, tmO2;

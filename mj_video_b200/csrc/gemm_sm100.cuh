@@ -53,6 +53,7 @@ struct GemmArgs {
     int seq;                   // QKV_VIT: tokens per tile (1025); PATCH: patches per tile (1024)
     int heads;                 // QKV_VIT: heads
     int v_hd;                  // QKV_LLM: columns per V head in N and rows per V^T plane (multiple of 32, <= 128)
+    int qk_slot;               // QKV_LLM: 128 (rotate-half partner 64 columns away) or 96 (partner in the adjacent column)
 };
 
 namespace gemm_detail {
@@ -442,6 +443,54 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             is_q ? args.out + static_cast<long long>(row) * args.ldo + n
                                  : args.out_k + static_cast<long long>(row) * args.n_k_cols + (n - args.n_q_cols);
                         const CUtensorMap* tm = is_q ? &tmO : &tmO2;
+                        if (args.qk_slot == 96) {
+                            // native head_dim 96: heads are three 32-column chunks wide and the rotary pair (d, d + 48) sits
+                            // in adjacent columns (2d, 2d + 1), so every chunk rotates on its own: chunk g of the q (or k)
+                            // columns belongs to head g / 3 and holds pairs (g % 3) * 16 ... + 15 of that head
+#pragma unroll 1
+                            for (int cp = 0; cp < 2; ++cp) {
+                                if (!kTma && cp != half) continue;   // BN == 128: each half does one 64-column box
+                                if (kTma) stg_wait();
+#pragma unroll 1
+                                for (int cc = 0; cc < 2; ++cc) {
+                                    const int c = cp * 64 + cc * 32;
+                                    uint32_t x[32];
+                                    ptx::tmem_ld_x32(t_base + h0 + c, x);
+                                    ptx::tmem_wait_ld();
+                                    uint32_t o[16];
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) o[i] = 0u;
+                                    if (row_ok) {
+                                        const int p0 = (((ncol + c) >> 5) % 3) * 16;
+                                        const float4* cs = reinterpret_cast<const float4*>(args.rope_cos + static_cast<long long>(pos) * 64 + p0);
+                                        const float4* sn = reinterpret_cast<const float4*>(args.rope_sin + static_cast<long long>(pos) * 64 + p0);
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i) {
+                                            const float4 cv = __ldg(cs + i);
+                                            const float4 sv = __ldg(sn + i);
+                                            const float cc4[4] = {cv.x, cv.y, cv.z, cv.w};
+                                            const float ss4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                                            for (int j = 0; j < 4; ++j) {
+                                                const float p1 = ptx::bf16_round(__uint_as_float(x[8 * i + 2 * j]));
+                                                const float p2 = ptx::bf16_round(__uint_as_float(x[8 * i + 2 * j + 1]));
+                                                // q*cos + rotate_half(q)*sin, each product and the sum rounded to bf16
+                                                const float a = ptx::bf16_round(p1 * cc4[j]) + ptx::bf16_round(-p2 * ss4[j]);
+                                                const float b = ptx::bf16_round(p2 * cc4[j]) + ptx::bf16_round(p1 * ss4[j]);
+                                                o[4 * i + j] = ptx::pack_bf16x2(a, b);
+                                            }
+                                        }
+                                    }
+                                    if constexpr (kTma) {
+                                        stg_put(cc, o);
+                                    } else {
+                                        if (row_ok) store32_bf16(dst + c, o);
+                                    }
+                                }
+                                if constexpr (kTma) stg_store(tm, ncol + cp * 64, m0 + q * 32);
+                            }
+                            continue;
+                        }
                         uint32_t hi_keep[2][16];  // rotated second halves (columns 64..127), stored after the first box
 #pragma unroll
                         for (int cp = 0; cp < 2; ++cp) {

@@ -26,7 +26,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None, *, e
          bias=None, residual=None, scale=None, block_n: int = 0, out_k=None, out_vt=None, rope_cos=None,
          rope_sin=None, row_pos=None, row_map=None, row_vt=None, pos_emb=None, n_q_cols: int = 0, n_k_cols: int = 0,
          vt_stride_head: int = 0, vt_ld: int = 0, seq: int = 0, heads: int = 0, ldo: int | None = None,
-         K: int | None = None, cta_group: int = 0, v_head_dim: int = 0) -> torch.Tensor:
+         K: int | None = None, cta_group: int = 0, v_head_dim: int = 0, qk_head_slot: int = 0) -> torch.Tensor:
     """D = A · Wᵀ with a fused epilogue (tcgen05 / TMEM / TMA). a: [M, K] bf16, w: [N, K] bf16 (nn.Linear layout)."""
     lib = _lib.load()
     _bf16(a, "a"), _bf16(w, "w")
@@ -56,13 +56,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None, *, e
     d.vt_stride_head, d.vt_ld, d.seq, d.heads = vt_stride_head, vt_ld, seq, heads
     d.cta_group = cta_group
     d.v_head_dim = v_head_dim
+    d.qk_head_slot = qk_head_slot
     _lib.check(lib.mjv_gemm_bf16(C.byref(d), _lib.current_stream()))
     return out
 
 
 def attention(q, k, vt, out, *, head_dim, heads, kv_heads, causal, scale, q_col0=0, k_col0=0, nseq=0, seq_len=0,
               cu_seqlens=None, work=None, vt_ld=None, vt_plane_stride=None, vt_starts=None, vt_cols=0, v_head_dim=0,
-              out_head_dim=0):
+              out_head_dim=0, qk_head_stride=0):
     """Fused attention. Batched mode: q/k are [nseq*seq_len, ld] and vt is [nseq*heads, head_dim, vt_ld].
     Varlen mode: packed rows with device int32 cu_seqlens[nseq+1] and work[(seq, q_block)] pairs; vt is
     [kv_heads, head_dim, vt_ld]."""
@@ -83,6 +84,7 @@ def attention(q, k, vt, out, *, head_dim, heads, kv_heads, causal, scale, q_col0
     d.n_work = 0 if work is None else work.shape[0]
     d.scale = scale
     d.v_head_dim, d.out_head_dim = v_head_dim, out_head_dim
+    d.qk_head_stride = qk_head_stride
     _lib.check(lib.mjv_attention(C.byref(d), _lib.current_stream()))
     return out
 

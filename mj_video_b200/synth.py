@@ -107,6 +107,13 @@ def dims_tiny_llama() -> ModelDims:
                      llm_kv_heads=2, gating_hidden=128, rope_theta=10000.0)
 
 
+def dims_tiny_llama_mha() -> ModelDims:
+    """dims_tiny_llama with 4 kv heads: head counts that are multiples of 4 take the native 96-wide q/k slot of the engine."""
+    d = dims_tiny_llama()
+    d.name, d.llm_kv_heads = "tiny-llama-mha", 4
+    return d
+
+
 def dims_tiny() -> ModelDims:
     """Small model with the same structure and the same ragged shapes (S=1025, head dims 64/128) for fast parity."""
     return ModelDims(name="tiny", vit_hidden=128, vit_heads=2, vit_mlp=256, vit_layers=2, llm_hidden=256,

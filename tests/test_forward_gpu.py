@@ -355,6 +355,26 @@ def test_llama_branch_head_dim_96_vs_reference_golden(gpu, golden_llama_forward)
     _check(out, o32)
 
 
+def test_native_head_dim_96_slot_vs_oracle(gpu):
+    """Llama-layout model with head_dim 96 and head counts that are multiples of 4: the engine packs q / k heads 96 columns
+    apart (rotary pairs in adjacent columns, no pad columns in the QKV GEMM, 6 of 8 k-steps in attention). Ragged batch
+    against the oracle in bf16 and fp32; the 4-head / 2-kv-head model next to it keeps the padded 128-wide slot."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from mj_video_b200.engine import Engine, EngineDims
+    from oracle import port
+    pv = torch.cat([load_video(synth.make_video(500 + i), num_segments=8, max_num=1, device="cuda", dtype=torch.bfloat16)[0]
+                    for i in range(3)])
+    ids, mask = synth.pad_batch([synth.make_input_ids(i, [1] * 8, n_cap=n) for i, n in enumerate([7, 90, 41])])
+    for d in (synth.dims_tiny_llama_mha(), synth.dims_tiny_llama()):
+        sd = synth.make_state_dict(d, seed=21, include_lm_head=False)
+        eng = Engine(EngineDims.from_synth(d), gpu)
+        eng.load_state_dict(sd)
+        mine = _as_dict(d, eng.forward(pv, ids, mask, synth.PAD, synth.IMG_CONTEXT))
+        _check(mine, port.Oracle(d, sd, dtype=torch.bfloat16, device=gpu).forward(pv, ids, mask))
+        _check(mine, port.Oracle(d, sd, dtype=torch.float32, device=gpu, inv_freq_dtype=torch.bfloat16).forward(pv.float(), ids, mask))
+
+
 def test_config5_widths_vs_oracle(gpu):
     """BASELINE configs[4] LLM widths (d 3072, 32 heads x 96, MHA, inter 8192, theta 1e4) with the layer counts cut to
     keep the oracle fast: 2 rows x 8 frames against the oracle in bf16 and fp32."""

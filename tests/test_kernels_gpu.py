@@ -166,6 +166,44 @@ def test_gemm_qkv_llm_packed_v_heads(ops):
     close(vt[:, :, :tot], y[:, (Hq + Hkv) * 128:].reshape(tot, Hkv, hv).permute(1, 2, 0))
 
 
+@pytest.mark.parametrize("block_n", [0, 128])
+def test_gemm_qkv_llm_native_head_dim_96(ops, block_n):
+    """QKV_LLM with the native head_dim-96 slot (mjv_gemm_desc.qk_head_slot = 96): q / k heads are 96 columns wide, the
+    rotary pair (d, d + 48) sits in adjacent columns (2d, 2d + 1) - the weight rows are stored in that order - and no column
+    of N is padding. Compared with rotate-half RoPE on the un-permuted projection."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    tot, D, Hq, Hkv, hd = 700, 256, 8, 4, 96
+    perm = torch.tensor([(j // 2) + 48 * (j % 2) for j in range(hd)], device="cuda")   # slot column j <- head dim perm[j]
+    x = (torch.randn(tot, D, device="cuda", generator=g) * 0.5).bfloat16()
+    w_ref = (torch.randn((Hq + 2 * Hkv) * hd, D, device="cuda", generator=g) * 0.1).bfloat16()   # [q heads | k heads | v heads]
+    wq = w_ref[:Hq * hd].reshape(Hq, hd, D)[:, perm].reshape(Hq * hd, D)
+    wk = w_ref[Hq * hd:(Hq + Hkv) * hd].reshape(Hkv, hd, D)[:, perm].reshape(Hkv * hd, D)
+    w = torch.cat([wq, wk, w_ref[(Hq + Hkv) * hd:]]).contiguous()      # N = 1536 = 6 x 256
+    pos = (torch.arange(tot, device="cuda") % 333).int()
+    inv = 1.0 / (1e4 ** (torch.arange(0, hd, 2, device="cuda").float() / hd))
+    fr = torch.outer(torch.arange(512, device="cuda").float(), inv)
+    cos = torch.ones(512, 64, device="cuda")
+    sin = torch.zeros(512, 64, device="cuda")
+    cos[:, :48], sin[:, :48] = fr.cos().bfloat16().float(), fr.sin().bfloat16().float()
+    vt_cols = (tot + 7) // 8 * 8
+    qo = torch.zeros(tot, Hq * hd, device="cuda", dtype=torch.bfloat16)
+    ko = torch.zeros(tot, Hkv * hd, device="cuda", dtype=torch.bfloat16)
+    vt = torch.zeros(Hkv, hd, vt_cols, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, w, out=qo, epilogue=ops.EPI_QKV_LLM, out_k=ko, out_vt=vt, rope_cos=cos.contiguous(), rope_sin=sin.contiguous(),
+             row_pos=pos, n_q_cols=Hq * hd, n_k_cols=Hkv * hd, vt_stride_head=hd * vt_cols, vt_ld=vt_cols, v_head_dim=hd,
+             qk_head_slot=96, block_n=block_n)
+    y = mm(x, w_ref).bfloat16()
+
+    def rope(t):   # t [tot, heads, 96] in the model's own order
+        c = torch.cat([cos[:, :48], cos[:, :48]], -1)[pos.long()].bfloat16()[:, None, :]
+        s_ = torch.cat([sin[:, :48], sin[:, :48]], -1)[pos.long()].bfloat16()[:, None, :]
+        return (t * c) + (torch.cat([-t[..., 48:], t[..., :48]], -1) * s_)
+
+    close(qo, rope(y[:, :Hq * hd].reshape(tot, Hq, hd))[..., perm].reshape(tot, -1))
+    close(ko, rope(y[:, Hq * hd:(Hq + Hkv) * hd].reshape(tot, Hkv, hd))[..., perm].reshape(tot, -1))
+    close(vt[:, :, :tot], y[:, (Hq + Hkv) * hd:].reshape(tot, Hkv, hd).permute(1, 2, 0))
+
+
 def ref_attn(q, k, v, causal, scale):
     H, Hkv = q.shape[1], k.shape[1]
     k = k.repeat_interleave(H // Hkv, dim=1)
@@ -251,6 +289,36 @@ def test_attention_narrow_heads_packed_v_and_output(ops):
     refs, o = [], 0
     for n in lens:
         refs.append(ref_attn(q[o:o + n, :, :hd].float(), k[o:o + n, :, :hd].float(), v[o:o + n].float(), True, 1 / math.sqrt(hd)))
+        o += n
+    assert (out.float() - torch.cat(refs)).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("lens,H,Hkv", [([300, 77, 129], 4, 2), ([2187, 640, 1], 8, 8), ([513], 3, 1)])
+def test_attention_packed_head_dim_96(ops, lens, H, Hkv):
+    """Native head_dim 96 (mjv_attn_desc.qk_head_stride = 96): q / k heads packed 96 columns apart under the 128-wide tile;
+    the tile's last 32 columns hold the NEXT head (or TMA zero fill after the last one) and must not enter Q.K^T."""
+    hd = 96
+    g = torch.Generator(device="cuda").manual_seed(12)
+    tot = sum(lens)
+    q = torch.randn(tot, H, hd, device="cuda", generator=g).bfloat16()
+    k = torch.randn(tot, Hkv, hd, device="cuda", generator=g).bfloat16()
+    v = torch.randn(tot, Hkv, hd, device="cuda", generator=g).bfloat16()
+    starts, vt_cols = ops.vt_layout(lens)
+    vt = torch.zeros(Hkv, hd, vt_cols, device="cuda", dtype=torch.bfloat16)
+    o = 0
+    for st, n in zip(starts, lens):
+        vt[:, :, st:st + n] = v[o:o + n].permute(1, 2, 0)
+        o += n
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    out = torch.full((tot, H * hd), 7.0, device="cuda", dtype=torch.bfloat16)
+    pair = (H // Hkv) % 2 == 1
+    ops.attention(q.reshape(tot, -1), k.reshape(tot, -1), vt, out, head_dim=128, heads=H, kv_heads=Hkv, causal=True,
+                  scale=1 / math.sqrt(hd), cu_seqlens=cu, work=ops.causal_work_list(lens, pair_blocks=pair).cuda(),
+                  vt_starts=torch.tensor(starts, dtype=torch.int32, device="cuda"), vt_cols=vt_cols, v_head_dim=hd,
+                  out_head_dim=hd, qk_head_stride=hd)
+    refs, o = [], 0
+    for n in lens:
+        refs.append(ref_attn(q[o:o + n].float(), k[o:o + n].float(), v[o:o + n].float(), True, 1 / math.sqrt(hd)))
         o += n
     assert (out.float() - torch.cat(refs)).abs().max().item() < 2e-2
 

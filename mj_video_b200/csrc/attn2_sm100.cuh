@@ -810,7 +810,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             // lane issues tcgen05.mma / tcgen05.commit. MMAs of different threads are not ordered against each other, so
             // the reuse of a score buffer is explicit: the S issuer waits for pv_done[b] of the step that last read it.
             const bool leader = ptx::elect_one();
-            constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD);
+            // N of P.V = rows of the V^T plane that exist (a multiple of 16; 96 for head_dim 96: the zero-filled rows are skipped)
+            const uint32_t idesc_o = ptx::make_idesc_bf16(BQ, args.pv_n);
             const uint64_t v_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sV));
             [[maybe_unused]] const uint64_t p_desc0 = ptx::make_desc_sw128(ptx::smem_u32(sP));
             int vst = 0;

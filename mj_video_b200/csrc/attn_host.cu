@@ -117,6 +117,7 @@ int attention(const mjv_attn_desc& d, cudaStream_t stream) {
     a.out_hd = out_hd;
     a.qk_stride = qk_stride;
     a.qk_ksteps = qk_stride / 16;
+    a.pv_n = (v_hd + 15) / 16 * 16;
 
     // algorithmic FLOPs: 4*heads*hd*S^2 per sequence (bidirectional); causal work is supplied by the caller (flops_hint)
     double work = d.flops_hint;

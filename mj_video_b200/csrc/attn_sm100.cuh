@@ -48,6 +48,7 @@ struct AttnArgs {
     int qk_stride;          // attention2: columns from one q / k head to the next in their tensors (= HD, or 96 for packed
                             // head_dim-96 heads under the 128-wide tile)
     int qk_ksteps;          // attention2: 16-column k-steps of Q.K^T that hold real columns (HD / 16, or 6 of 8 for head_dim 96)
+    int pv_n;               // attention2: N of the P.V MMA = V^T rows that exist, rounded up to 16 (<= HD)
     int kv_tail;            // attention2, batched bidirectional head_dim 64, seq_len % 128 == 1 (ViT: 1025): the last key is folded
                             // in on the CUDA cores (softmax warps: q.k_last; epilogue: + p_last * v_last) instead of costing
                             // every item a ninth 128-column step with one valid column

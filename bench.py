@@ -297,12 +297,15 @@ def run_mjv(args):
     # the data-path collective goes through the library's own C ABI (mjv_allgather_scores -> ncclAllGather over NVLink)
     gather = NcclScoreGather(dev) if world > 1 else None
 
-    def step_resident():
+    def step_local():   # this rank's kernels only: no collective (the rank-0-only breakdown step below must not hang the others)
         preprocess_frames(frames_dev, 448, max_num, True, torch.bfloat16, out=px)
-        out = eng.run(sb)
+        return eng.run(sb)["scores"]
+
+    def step_resident():
+        scores = step_local()
         if world > 1:
-            return gather.gather(out["scores"], n_pairs_total)
-        return out["scores"]
+            return gather.gather(scores, n_pairs_total)
+        return scores
 
     if world > 1:  # the C-ABI collective agrees with torch.distributed's on the same table
         chk = eng.run(sb)["scores"]
@@ -400,7 +403,7 @@ def run_mjv(args):
     roofline_kernels = None
     if rank == 0:
         lib.mjv_profile_enable(_lib.tag_mask())
-        step_resident()
+        step_local()
         torch.cuda.synchronize()
         lib.mjv_profile_enable(0)
         agg, by_tag = {}, {}

@@ -159,6 +159,7 @@ AxisCoeffs make_coeffs(int in_size, int out_size) {
 struct DeviceCoeffs {
     int ksize = 0;
     int out_size = 0;
+    bool fits_s24 = true;   // every coefficient within (-2^23, 2^23): the fused kernel's three byte planes hold it
     int* bounds = nullptr;
     int* kk = nullptr;
     const std::vector<int>* host_bounds = nullptr;   // [out][2], owned by the cache
@@ -192,6 +193,7 @@ int get_device_coeffs(int in_size, int out_size, cudaStream_t st, DeviceCoeffs* 
     d.ksize = c.ksize;
     d.out_size = out_size;
     d.host_bounds = new std::vector<int>(c.bounds);   // library-owned like the device tables
+    for (int v : c.kk) d.fits_s24 = d.fits_s24 && v > -(1 << 23) && v < (1 << 23);
     MJV_CUDA_OK(cudaMalloc(&d.bounds, c.bounds.size() * sizeof(int)));
     MJV_CUDA_OK(cudaMalloc(&d.kk, c.kk.size() * sizeof(int)));
     MJV_CUDA_OK(cudaMemcpyAsync(d.bounds, c.bounds.data(), c.bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -285,7 +287,7 @@ resample_v_tiles_kernel(const uint8_t* __restrict__ tmp, TOut* __restrict__ out,
 // this kernel for real video sizes (frame path).
 struct FusedGeom {
     int F, H, W, OW, OH, S, gi, tiles_per_frame, tile_offset;
-    int BW, BH, ksh, ksh4, ksv;
+    int BW, BH, ksh, ksh4, ksv, ksv4;
     int stage_stride;   // bytes per staged input row (multiple of 4, = 4 mod 128)
     int stage_bytes;    // staging area (also holds the BH x 3*BW output bytes between phases 2 and 3)
     int rmax;           // rows of hbuf
@@ -302,17 +304,39 @@ __device__ __forceinline__ uint32_t load_word_guarded(const uint8_t* p, const ui
         if (p + b < end) v |= static_cast<uint32_t>(p[b]) << (8 * b);
     return v;
 }
-template <int B>
-__device__ __forceinline__ int byte_of(uint32_t w) { return static_cast<int>(__byte_perm(w, 0, 0x4440 | B)); }
+// Coefficients are 22-bit fixed point (|k| < 2^23): k = k0 + 256 k1 + 65536 k2 with k0, k1 unsigned bytes and k2 a signed
+// byte. Four taps of one colour channel are gathered into one register (PRMT) and multiplied plane by plane with dp4a; the
+// three partial sums recombine to exactly Pillow's 32-bit accumulator (two's-complement arithmetic modulo 2^32, and the true
+// sum fits in 32 bits as it does in Pillow): 15 instructions for 12 multiply-adds instead of 24.
+__device__ __forceinline__ int4 split_coeffs(int c0, int c1, int c2, int c3) {
+    const uint32_t u0 = static_cast<uint32_t>(c0), u1 = static_cast<uint32_t>(c1), u2 = static_cast<uint32_t>(c2),
+                   u3 = static_cast<uint32_t>(c3);
+    int4 r;
+    r.x = static_cast<int>((u0 & 0xffu) | ((u1 & 0xffu) << 8) | ((u2 & 0xffu) << 16) | ((u3 & 0xffu) << 24));
+    r.y = static_cast<int>(((u0 >> 8) & 0xffu) | (((u1 >> 8) & 0xffu) << 8) | (((u2 >> 8) & 0xffu) << 16) | (((u3 >> 8) & 0xffu) << 24));
+    r.z = static_cast<int>(((u0 >> 16) & 0xffu) | (((u1 >> 16) & 0xffu) << 8) | (((u2 >> 16) & 0xffu) << 16) | (((u3 >> 16) & 0xffu) << 24));
+    r.w = 0;
+    return r;
+}
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, int b, uint32_t c) { return __dp4a(a, static_cast<uint32_t>(b), c); }
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint8_t finish_taps(uint32_t a0, uint32_t a1, int a2) {
+    const uint32_t sum = (1u << 21) + a0 + (a1 << 8) + (static_cast<uint32_t>(a2) << 16);
+    return clip8(static_cast<int>(sum) >> 22);
+}
 
 template <typename TOut>
 __global__ void __launch_bounds__(256)
 resample_fused_kernel(const uint8_t* __restrict__ in, TOut* __restrict__ out, const FusedGeom g, const NormLut lut_arg) {
     extern __shared__ __align__(16) uint8_t fsm[];
     float* lut = reinterpret_cast<float*>(fsm);                       // [768]
-    int* kh = reinterpret_cast<int*>(fsm + 3072);                     // [BW][ksh4], zero padded
-    int* kv = kh + g.BW * g.ksh4;                                     // [BH][ksv]
-    int* bh = kv + g.BH * g.ksv;                                      // [BW][2]
+    int4* kh4 = reinterpret_cast<int4*>(fsm + 3072);                  // [BW][ksh4 / 4]: byte planes of 4 taps, zero padded
+    int4* kv4 = kh4 + g.BW * (g.ksh4 >> 2);                           // [BH][ksv4 / 4]
+    int* bh = reinterpret_cast<int*>(kv4 + g.BH * (g.ksv4 >> 2));     // [BW][2]
     int* bv = bh + 2 * g.BW;                                          // [BH][2]
     uint8_t* hbuf = reinterpret_cast<uint8_t*>(bv + 2 * g.BH);        // [rmax][kHbufStride]
     uint8_t* stage = hbuf + ((g.rmax * kHbufStride + 15) & ~15);      // [32][stage_stride]
@@ -324,13 +348,21 @@ resample_fused_kernel(const uint8_t* __restrict__ in, TOut* __restrict__ out, co
     const int gx0 = bx * g.BW, gy0 = by * g.BH;
     const int bw = min(g.BW, g.OW - gx0), bhh = min(g.BH, g.OH - gy0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gh = g.ksh4 >> 2, gv = g.ksv4 >> 2;
 
     for (int i = tid; i < 768; i += 256) lut[i] = lut_arg.v[i];
-    for (int i = tid; i < bw * g.ksh4; i += 256) {
-        const int ox = i / g.ksh4, x = i - ox * g.ksh4;
-        kh[i] = x < g.ksh ? g.kk_h[static_cast<long long>(gx0 + ox) * g.ksh + x] : 0;
+    for (int i = tid; i < bw * gh; i += 256) {
+        const int ox = i / gh, x4 = (i - ox * gh) * 4;
+        const int* src = g.kk_h + static_cast<long long>(gx0 + ox) * g.ksh;
+        kh4[i] = split_coeffs(x4 < g.ksh ? src[x4] : 0, x4 + 1 < g.ksh ? src[x4 + 1] : 0, x4 + 2 < g.ksh ? src[x4 + 2] : 0,
+                              x4 + 3 < g.ksh ? src[x4 + 3] : 0);
     }
-    for (int i = tid; i < bhh * g.ksv; i += 256) kv[i] = g.kk_v[static_cast<long long>(gy0) * g.ksv + i];
+    for (int i = tid; i < bhh * gv; i += 256) {
+        const int oy = i / gv, y4 = (i - oy * gv) * 4;
+        const int* src = g.kk_v + static_cast<long long>(gy0 + oy) * g.ksv;
+        kv4[i] = split_coeffs(y4 < g.ksv ? src[y4] : 0, y4 + 1 < g.ksv ? src[y4 + 1] : 0, y4 + 2 < g.ksv ? src[y4 + 2] : 0,
+                              y4 + 3 < g.ksv ? src[y4 + 3] : 0);
+    }
     for (int i = tid; i < 2 * bw; i += 256) bh[i] = g.bounds_h[2 * gx0 + i];
     for (int i = tid; i < 2 * bhh; i += 256) bv[i] = g.bounds_v[2 * gy0 + i];
     __syncthreads();
@@ -385,45 +417,61 @@ resample_fused_kernel(const uint8_t* __restrict__ in, TOut* __restrict__ out, co
                 const int boff = (bh[2 * ox] - x_lo) * 3, n = bh[2 * ox + 1];   // warp-uniform
                 const int sh = (boff & 3) * 8;
                 const uint32_t* wp = row + (boff >> 2);
-                const int4* kp = reinterpret_cast<const int4*>(kh + ox * g.ksh4);
-                int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+                const int4* kp = kh4 + ox * gh;
+                uint32_t r0a = 0, r1a = 0, g0a = 0, g1a = 0, b0a = 0, b1a = 0;
+                int r2a = 0, g2a = 0, b2a = 0;
                 for (int x4 = 0; x4 < n; x4 += 4) {
                     const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
                     wp += 3;
+                    // 12 stream bytes = 4 taps x RGB
                     const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh),
                                    v2 = __funnelshift_r(w2, w3, sh);
                     const int4 k = *kp++;   // taps beyond n are zero
-                    s0 += byte_of<0>(v0) * k.x; s1 += byte_of<1>(v0) * k.x; s2 += byte_of<2>(v0) * k.x;
-                    s0 += byte_of<3>(v0) * k.y; s1 += byte_of<0>(v1) * k.y; s2 += byte_of<1>(v1) * k.y;
-                    s0 += byte_of<2>(v1) * k.z; s1 += byte_of<3>(v1) * k.z; s2 += byte_of<0>(v2) * k.z;
-                    s0 += byte_of<1>(v2) * k.w; s1 += byte_of<2>(v2) * k.w; s2 += byte_of<3>(v2) * k.w;
+                    const uint32_t r4 = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);   // bytes 0, 3, 6, 9
+                    const uint32_t g4 = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);   // bytes 1, 4, 7, 10
+                    const uint32_t b4 = __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410);   // bytes 2, 5, 8, 11
+                    r0a = dp4a_uu(r4, k.x, r0a); r1a = dp4a_uu(r4, k.y, r1a); r2a = dp4a_us(r4, k.z, r2a);
+                    g0a = dp4a_uu(g4, k.x, g0a); g1a = dp4a_uu(g4, k.y, g1a); g2a = dp4a_us(g4, k.z, g2a);
+                    b0a = dp4a_uu(b4, k.x, b0a); b1a = dp4a_uu(b4, k.y, b1a); b2a = dp4a_us(b4, k.z, b2a);
                 }
-                hrow[ox * 3 + 0] = clip8(s0 >> 22);
-                hrow[ox * 3 + 1] = clip8(s1 >> 22);
-                hrow[ox * 3 + 2] = clip8(s2 >> 22);
+                hrow[ox * 3 + 0] = finish_taps(r0a, r1a, r2a);
+                hrow[ox * 3 + 1] = finish_taps(g0a, g1a, g2a);
+                hrow[ox * 3 + 2] = finish_taps(b0a, b1a, b2a);
             }
         }
         __syncthreads();
     }
-    // ---- vertical taps: one word = 4 interleaved bytes of a horizontal-pass row per thread; results parked as bytes
+    // ---- vertical taps: one word = 4 interleaved bytes of a horizontal-pass row per thread, four rows per dp4a (the 4 x 4
+    // byte transpose costs 8 PRMTs); results parked as bytes
     uint32_t* obuf = reinterpret_cast<uint32_t*>(stage);   // [BH][48] words
     constexpr int kRowWords = 48;                          // 64 pixels x 3 bytes
+    constexpr int kHW = kHbufStride / 4;
     for (int item = tid; item < bhh * kRowWords; item += 256) {
         const int oy = item / kRowWords, wi = item - oy * kRowWords;
         const int ymin = bv[2 * oy] - y_lo, n = bv[2 * oy + 1];
-        const int* k = kv + oy * g.ksv;
+        const int4* kq = kv4 + oy * gv;
         const uint32_t* p = reinterpret_cast<const uint32_t*>(hbuf + ymin * kHbufStride) + wi;
-        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21, a3 = 1 << 21;
-        for (int y = 0; y < n; ++y) {
-            const uint32_t w = p[y * (kHbufStride / 4)];
-            const int kk = k[y];
-            a0 += byte_of<0>(w) * kk;
-            a1 += byte_of<1>(w) * kk;
-            a2 += byte_of<2>(w) * kk;
-            a3 += byte_of<3>(w) * kk;
+        uint32_t a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+        int a2[4] = {0, 0, 0, 0};
+        for (int y4 = 0; y4 < n; y4 += 4) {
+            const uint32_t w0 = p[0], w1 = p[kHW], w2 = p[2 * kHW], w3 = p[3 * kHW];   // rows beyond n: zero coefficients
+            p += 4 * kHW;
+            const uint32_t t01 = __byte_perm(w0, w1, 0x5140), t23 = __byte_perm(w2, w3, 0x5140);
+            const uint32_t u01 = __byte_perm(w0, w1, 0x7362), u23 = __byte_perm(w2, w3, 0x7362);
+            const uint32_t c[4] = {__byte_perm(t01, t23, 0x5410), __byte_perm(t01, t23, 0x7632),
+                                   __byte_perm(u01, u23, 0x5410), __byte_perm(u01, u23, 0x7632)};
+            const int4 k = *kq++;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                a0[b] = dp4a_uu(c[b], k.x, a0[b]);
+                a1[b] = dp4a_uu(c[b], k.y, a1[b]);
+                a2[b] = dp4a_us(c[b], k.z, a2[b]);
+            }
         }
-        obuf[item] = static_cast<uint32_t>(clip8(a0 >> 22)) | (static_cast<uint32_t>(clip8(a1 >> 22)) << 8) |
-                     (static_cast<uint32_t>(clip8(a2 >> 22)) << 16) | (static_cast<uint32_t>(clip8(a3 >> 22)) << 24);
+        obuf[item] = static_cast<uint32_t>(finish_taps(a0[0], a1[0], a2[0])) |
+                     (static_cast<uint32_t>(finish_taps(a0[1], a1[1], a2[1])) << 8) |
+                     (static_cast<uint32_t>(finish_taps(a0[2], a1[2], a2[2])) << 16) |
+                     (static_cast<uint32_t>(finish_taps(a0[3], a1[3], a2[3])) << 24);
     }
     __syncthreads();
     // ---- crop + LUT + planar store: lane = output column of one colour plane
@@ -454,17 +502,18 @@ resample_fused_kernel(const uint8_t* __restrict__ in, TOut* __restrict__ out, co
 bool plan_fused(int F, int H, int W, int OW, int OH, int S, int gi, int tpf, int tile_offset, const DeviceCoeffs& ch,
                 const DeviceCoeffs& cv, FusedGeom* out_g, size_t* out_smem, long long* out_ctas) {
     constexpr size_t kMaxSmem = 200 * 1024;
+    if (!ch.fits_s24 || !cv.fits_s24) return false;
     for (int BH = 32; BH >= 8; BH >>= 1) {
         FusedGeom g;
         g.F = F; g.H = H; g.W = W; g.OW = OW; g.OH = OH; g.S = S; g.gi = gi; g.tiles_per_frame = tpf; g.tile_offset = tile_offset;
-        g.BW = kFusedBW; g.BH = BH; g.ksh = ch.ksize; g.ksh4 = (ch.ksize + 3) & ~3; g.ksv = cv.ksize;
+        g.BW = kFusedBW; g.BH = BH; g.ksh = ch.ksize; g.ksh4 = (ch.ksize + 3) & ~3; g.ksv = cv.ksize; g.ksv4 = (cv.ksize + 3) & ~3;
         g.bounds_h = ch.bounds; g.kk_h = ch.kk; g.bounds_v = cv.bounds; g.kk_v = cv.kk;
         g.in_bytes = (long long)F * H * W * 3;
         const int seg = ch.max_span(g.BW) * 3 + 24;                // + rounding to whole words and the 4-word read-ahead
         g.stage_stride = ((seg + 127) / 128) * 128 + 4;
         g.stage_bytes = std::max(32 * g.stage_stride, BH * 3 * g.BW);
-        g.rmax = cv.max_span(BH);
-        const size_t smem = 3072 + 4 * (size_t)(g.BW * g.ksh4 + BH * g.ksv + 2 * g.BW + 2 * BH) +
+        g.rmax = cv.max_span(BH) + 3;                              // the vertical pass reads rows four at a time
+        const size_t smem = 3072 + 4 * (size_t)(g.BW * g.ksh4 + BH * g.ksv4 + 2 * g.BW + 2 * BH) +
                             (((size_t)g.rmax * kHbufStride + 15) & ~(size_t)15) + (size_t)g.stage_bytes;
         const long long ctas = (long long)F * ((OW + g.BW - 1) / g.BW) * ((OH + BH - 1) / BH);
         if (smem > kMaxSmem || ctas <= 0 || ctas >= (1LL << 31)) continue;

@@ -507,3 +507,30 @@ def test_longrope_tables_match_transformers():
     import pytest
     with pytest.raises(ValueError):
         longrope_inv_freq(dataclasses.replace(d, rope_short_factor=(1.0,)), hd, 10)
+
+
+def test_bench_rank0_only_sections_issue_no_collective():
+    """bench.py at N > 1: every rank must reach every collective. The per-kernel breakdown step and the CPU baseline run on
+    rank 0 only, so they must use the rank-local step (no all-gather) - a breakdown step that ended in the NCCL all-gather
+    hung every multi-GPU run of one build of this round."""
+    import ast
+    import pathlib
+    src = pathlib.Path(__file__).resolve().parents[1].joinpath("bench.py").read_text()
+    tree = ast.parse(src)
+    run_mjv = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "run_mjv")
+    collective_names = {"step_resident", "step_e2e", "barrier", "gather", "allgather_scores", "all_gather_into_tensor",
+                        "all_reduce", "broadcast"}
+
+    def is_rank0_test(t):
+        return (isinstance(t, ast.Compare) and isinstance(t.left, ast.Name) and t.left.id == "rank") or \
+               (isinstance(t, ast.BoolOp) and any(is_rank0_test(v) for v in t.values))
+
+    checked = 0
+    for node in ast.walk(run_mjv):
+        if isinstance(node, ast.If) and is_rank0_test(node.test):
+            checked += 1
+            for sub in node.body:
+                for call in (c for c in ast.walk(sub) if isinstance(c, ast.Call)):
+                    name = call.func.id if isinstance(call.func, ast.Name) else getattr(call.func, "attr", "")
+                    assert name not in collective_names, f"bench.py line {call.lineno}: {name}() inside a rank-0-only block"
+    assert checked >= 2   # the breakdown block and the JSON print at least

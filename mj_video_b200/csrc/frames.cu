@@ -330,7 +330,7 @@ __device__ __forceinline__ uint8_t finish_taps(uint32_t a0, uint32_t a1, int a2)
 }
 
 template <typename TOut>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 resample_fused_kernel(const uint8_t* __restrict__ in, TOut* __restrict__ out, const FusedGeom g, const NormLut lut_arg) {
     extern __shared__ __align__(16) uint8_t fsm[];
     float* lut = reinterpret_cast<float*>(fsm);                       // [768]
@@ -474,26 +474,31 @@ resample_fused_kernel(const uint8_t* __restrict__ in, TOut* __restrict__ out, co
                      (static_cast<uint32_t>(finish_taps(a0[3], a1[3], a2[3])) << 24);
     }
     __syncthreads();
-    // ---- crop + LUT + planar store: lane = output column of one colour plane
+    // ---- crop + LUT + planar store: one warp per (output row, colour plane), lane = output column - the row pointer is
+    // computed once per warp and the 2 x 32 elements of a plane row are contiguous in HBM
     const uint8_t* ob = reinterpret_cast<const uint8_t*>(obuf);
-    constexpr int per_row = 3 * kFusedBW;   // a multiple of 32: a warp stays inside one (row, plane)
     // S is a multiple of both block sizes in every geometry the reference produces (448): the block lies in one tile
     const bool one_tile = (g.S % kFusedBW == 0) && (g.S % g.BH == 0);
+    const long long tile_base = f * g.tiles_per_frame + g.tile_offset;
     const int tile0 = (gy0 / g.S) * g.gi + (gx0 / g.S), ty0 = gy0 % g.S, tx0 = gx0 % g.S;
-    for (int idx = tid; idx < bhh * per_row; idx += 256) {
-        const int oy = idx / per_row;
-        const int rem = idx - oy * per_row;
-        const int c = rem / kFusedBW, xo = rem - c * kFusedBW;
-        if (xo >= bw) continue;
-        const int v = ob[oy * (kRowWords * 4) + xo * 3 + c];
-        int tile = tile0, y = ty0 + oy, x = tx0 + xo;
-        if (!one_tile) {
-            const int gx = gx0 + xo, gy = gy0 + oy;
-            tile = (gy / g.S) * g.gi + (gx / g.S);
-            y = gy % g.S;
-            x = gx % g.S;
+    for (int rp = warp; rp < bhh * 3; rp += 8) {
+        const int oy = rp / 3, c = rp - oy * 3;
+        const uint8_t* orow = ob + oy * (kRowWords * 4) + c;
+        const float* lc = lut + c * 256;
+        if (one_tile) {
+            TOut* dst = out + (((tile_base + tile0) * 3 + c) * g.S + (ty0 + oy)) * g.S + tx0;
+#pragma unroll
+            for (int h2 = 0; h2 < kFusedBW / 32; ++h2) {
+                const int xo = h2 * 32 + lane;
+                if (xo < bw) dst[xo] = cvt_out<TOut>(lc[orow[xo * 3]]);
+            }
+        } else {
+            for (int xo = lane; xo < bw; xo += 32) {
+                const int gx = gx0 + xo, gy = gy0 + oy;
+                const int tile = (gy / g.S) * g.gi + (gx / g.S);
+                out[(((tile_base + tile) * 3 + c) * g.S + gy % g.S) * g.S + gx % g.S] = cvt_out<TOut>(lc[orow[xo * 3]]);
+            }
         }
-        out[(((f * g.tiles_per_frame + g.tile_offset + tile) * 3 + c) * g.S + y) * g.S + x] = cvt_out<TOut>(lut[c * 256 + v]);
     }
 }
 

@@ -218,7 +218,9 @@ def ref_attn(q, k, v, causal, scale):
 @pytest.mark.parametrize("T,S,H", [(1, 1, 1), (1, 128, 1), (2, 129, 2), (1, 257, 2), (3, 1025, 2),
                                    # S % 128 == 1 paths of attention2: last key on the CUDA cores (S > 512), odd last q-blocks
                                    # of two heads sharing an item (even head count, odd block count)
-                                   (1, 385, 2), (1, 513, 2), (2, 641, 2), (2, 1025, 3), (5, 1025, 4), (150, 1025, 2)])
+                                   (1, 385, 2), (1, 513, 2), (2, 641, 2), (2, 1025, 3), (5, 1025, 4), (150, 1025, 2),
+                                   # one q-block only / three q-blocks with an even head count: every item (or the last) is a head pair
+                                   (2, 100, 2), (3, 128, 4), (2, 300, 4), (40, 300, 8)])
 def test_attention_bidirectional(ops, T, S, H):
     """ViT shape (hd 64): ragged S incl. the 1-row tail block of S=1025 and the degenerate S=1."""
     g = torch.Generator(device="cuda").manual_seed(S)

@@ -274,9 +274,9 @@ resample_v_tiles_kernel(const uint8_t* __restrict__ tmp, TOut* __restrict__ out,
 // Fused resize: one CTA produces a BW x BH block of the resized frame. The horizontal pass runs over just the input rows
 // the block's vertical taps read and keeps its uint8 result (Pillow's intermediate image, same rounding) in shared memory;
 // the vertical pass, crop, LUT and planar store follow in the same CTA - the [F,H,OW,3] temporary never exists in HBM.
-//   stage:   32 input rows per pass, copied with aligned 4-byte loads and shifted so that every staged row starts on a word;
+//   stage:   32 input rows per pass, copied with 4-byte cp.async from the aligned word below each segment start;
 //   phase 1: lane = row, warp = output column. The taps of one output pixel are 3n contiguous bytes; they are read as
-//            words (4 taps = 3 words after a warp-uniform funnel shift) and the bytes picked with PRMT - a byte load per tap
+//            words (4 taps = 3 words after a funnel shift) and the bytes picked with PRMT - a byte load per tap
 //            and channel made the first version of this kernel shared-memory-issue bound (tools/frames_bench.py: 1.77 ms
 //            for 256 x 720p). Coefficients come 4 at a time (one 16-byte broadcast load). Lanes hit 32 different banks
 //            (row stride = 4 mod 128 bytes);
@@ -374,47 +374,34 @@ resample_fused_kernel(const uint8_t* __restrict__ in, TOut* __restrict__ out, co
     const uint8_t* in_end = in + g.in_bytes;
 
     for (int r0 = 0; r0 < rows; r0 += 32) {
-        // ---- stage up to 32 input row segments: warp w copies rows w, w+8, ... and shifts them onto a word boundary.
-        // All loads of a 256-word chunk are issued before the first store (the copy is latency bound otherwise); only the
-        // last row of the whole input can touch the end of the allocation and takes the guarded loads.
+        // ---- stage up to 32 input row segments: warp w copies rows w, w+8, ... with 4-byte cp.async from the aligned word at
+        // or below the segment start (no registers, no instructions waiting on the loads); the row's 0-3 lead bytes are
+        // absorbed by the per-lane funnel shift of the tap loop. Only the last row of the whole input can touch the end of
+        // the allocation and takes guarded synchronous loads.
         for (int r = warp; r < 32 && r0 + r < rows; r += 8) {
             const uint8_t* src = frame + (static_cast<long long>(y_lo + r0 + r) * g.W + x_lo) * 3;
             const int lead = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 3);
             const uint8_t* src_al = src - lead;
             uint32_t* dst4 = reinterpret_cast<uint32_t*>(stage + r * g.stage_stride);
             if (src_al + 4 * (seg_words + 1) <= in_end) {
-                const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src_al);
-                for (int base = 0; base < seg_words; base += 256) {
-                    uint32_t lo[8], hi[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int i = base + u * 32 + lane;
-                        if (i < seg_words) {
-                            lo[u] = __ldg(s4 + i);
-                            hi[u] = __ldg(s4 + i + 1);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int i = base + u * 32 + lane;
-                        if (i < seg_words) dst4[i] = __funnelshift_r(lo[u], hi[u], 8 * lead);
-                    }
-                }
+                const uint32_t dst_s = ptx::smem_u32(dst4);
+                for (int i = lane; i <= seg_words; i += 32)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_s + 4 * i), "l"(src_al + 4 * i) : "memory");
             } else {
-                for (int i = lane; i < seg_words; i += 32) {
-                    const uint32_t lo = load_word_guarded(src_al + 4 * i, in_end);
-                    const uint32_t hi = lead != 0 ? load_word_guarded(src_al + 4 * i + 4, in_end) : 0u;
-                    dst4[i] = __funnelshift_r(lo, hi, 8 * lead);
-                }
+                for (int i = lane; i <= seg_words; i += 32) dst4[i] = load_word_guarded(src_al + 4 * i, in_end);
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         // ---- horizontal taps: lane = staged row, warp = output column (w, w+8, ...)
         if (r0 + lane < rows) {
             const uint32_t* row = reinterpret_cast<const uint32_t*>(stage + lane * g.stage_stride);
             uint8_t* hrow = hbuf + (r0 + lane) * kHbufStride;
+            const int lead = static_cast<int>(
+                reinterpret_cast<uintptr_t>(frame + (static_cast<long long>(y_lo + r0 + lane) * g.W + x_lo) * 3) & 3);
             for (int ox = warp; ox < bw; ox += 8) {
-                const int boff = (bh[2 * ox] - x_lo) * 3, n = bh[2 * ox + 1];   // warp-uniform
+                const int boff = (bh[2 * ox] - x_lo) * 3 + lead, n = bh[2 * ox + 1];   // n is warp-uniform
                 const int sh = (boff & 3) * 8;
                 const uint32_t* wp = row + (boff >> 2);
                 const int4* kp = kh4 + ox * gh;

@@ -32,9 +32,12 @@ template <int W>
 __device__ __forceinline__ float row_sum(float v, float* red, int warp_in_block) {
     v = warp_sum(v);
     if (W == 1) return v;
-    __syncthreads();  // previous use of `red` is over
+    // the W warps of one row synchronise among themselves (named barrier 1 + row-in-block), not with the other rows of the
+    // block: a block-wide __syncthreads made every row wait for the slowest of the 4-8 rows four times per LayerNorm
+    const int bar_id = 1 + warp_in_block / W;
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(W * 32) : "memory");  // previous use of `red` is over
     if ((threadIdx.x & 31) == 0) red[warp_in_block] = v;
-    __syncthreads();
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(W * 32) : "memory");
     float t = 0.f;
     const int base = warp_in_block / W * W;
 #pragma unroll
@@ -204,19 +207,30 @@ gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict_
 // ------------------------------------------------------------------------------------------------ patch im2col
 // pixel_values [T,3,H,W] (bf16 or fp32) -> A[T*P, Kpad] bf16 with k = c*ps*ps + ky*ps + kx (the flattening of
 // nn.Conv2d's weight, modeling_intern_vit.py:164), zero padded to Kpad so rows are 16-byte aligned for TMA.
-// One block = one row of patches of one tile: the 3 x ps image rows it covers are staged in shared memory with coalesced
-// 16-byte loads (each image row is contiguous), then every thread assembles 8 consecutive k of one patch from shared
-// memory and issues one 16-byte store — both global streams are fully coalesced.
+// One block = one row of patches of one tile. The 3 x ps image rows it covers are read with coalesced 16-byte loads and
+// scattered into shared memory ALREADY in im2col order ([patch][k], 4-byte stores of the even-aligned element pairs; the
+// tile's row stride is padded so that the patches do not alias the same banks); every thread then moves 8 consecutive k of
+// one patch with one 16-byte shared load and one 16-byte global store. (The first version staged the image rows as they
+// are and gathered 2-byte elements: 8 bank-conflicted loads per thread kept the LSU busier than HBM, 4.2 TB/s.)
 template <typename TIn>
 __global__ void __launch_bounds__(512)
-im2col_kernel(const TIn* __restrict__ px, __nv_bfloat16* __restrict__ out, int T, int img, int ps, int Kpad) {
+im2col_kernel(const TIn* __restrict__ px, __nv_bfloat16* __restrict__ out, int T, int img, int ps, int Kpad, int kstride) {
     extern __shared__ __align__(16) unsigned char im2col_smem[];
-    __nv_bfloat16* rows_s = reinterpret_cast<__nv_bfloat16*>(im2col_smem);  // [3][ps][img]
+    __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(im2col_smem);  // [g][kstride], kstride >= Kpad
     const int g = img / ps;
     const int K = 3 * ps * ps;
     const int kvec = Kpad / 8;
     const int t = blockIdx.x / g, pi = blockIdx.x - t * g;
-    constexpr int VEC = 16 / sizeof(TIn);  // elements per 16-byte load
+    // zero the pad columns K .. Kpad of every patch (K and Kpad are even)
+    {
+        const int padw = (Kpad - K) >> 1;
+        uint32_t* t32 = reinterpret_cast<uint32_t*>(tile);
+        for (int i = threadIdx.x; i < g * padw; i += blockDim.x) {
+            const int pj = i / padw, w = i - pj * padw;
+            t32[(pj * kstride + K) / 2 + w] = 0u;
+        }
+    }
+    constexpr int VEC = 16 / sizeof(TIn);  // elements per 16-byte load (8 or 4: even, so pairs never straddle a patch)
     const int vec_per_row = img / VEC;
     const int n_vec = 3 * ps * vec_per_row;
     for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
@@ -224,37 +238,33 @@ im2col_kernel(const TIn* __restrict__ px, __nv_bfloat16* __restrict__ out, int T
         const int c = r / ps, ky = r - c * ps;
         const TIn* src = px + ((static_cast<size_t>(t) * 3 + c) * img + pi * ps + ky) * img + v * VEC;
         const uint4 raw = *reinterpret_cast<const uint4*>(src);
-        __nv_bfloat16* dst = rows_s + r * img + v * VEC;
+        uint32_t pairs[VEC / 2];
         if (sizeof(TIn) == 2) {
-            *reinterpret_cast<uint4*>(dst) = raw;
+            pairs[0] = raw.x;
+            pairs[1] = raw.y;
+            if (VEC == 8) {
+                pairs[VEC / 2 - 2] = raw.z;
+                pairs[VEC / 2 - 1] = raw.w;
+            }
         } else {
             const float* f = reinterpret_cast<const float*>(&raw);
-            *reinterpret_cast<uint2*>(dst) = make_uint2(ptx::pack_bf16x2(f[0], f[1]), ptx::pack_bf16x2(f[2], f[3]));
+            pairs[0] = ptx::pack_bf16x2(f[0], f[1]);
+            pairs[1] = ptx::pack_bf16x2(f[2], f[3]);
+        }
+        const int x0 = v * VEC;
+#pragma unroll
+        for (int q = 0; q < VEC / 2; ++q) {
+            const int x = x0 + 2 * q;            // even; ps is even, so x and x + 1 lie in the same patch
+            const int pj = x / ps, kx = x - pj * ps;
+            *reinterpret_cast<uint32_t*>(tile + pj * kstride + r * ps + kx) = pairs[q];
         }
     }
     __syncthreads();
-    // blockDim.x is a multiple of kvec: a thread always produces the same 8 k of successive patches, so the k -> (row,
-    // column) decomposition (integer divisions) is done once, outside the loop
     const int kv = threadIdx.x % kvec;
-    const int k0 = kv * 8;
-    int off[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int k = k0 + e;
-        const int r = k / ps;  // c*ps + ky
-        off[e] = k < K ? r * img + (k - r * ps) : -1;
-    }
-    const unsigned short* rs = reinterpret_cast<const unsigned short*>(rows_s);
     for (int pj = threadIdx.x / kvec; pj < g; pj += blockDim.x / kvec) {
-        uint32_t packed[4];
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-            const unsigned short lo = off[e] >= 0 ? rs[off[e] + pj * ps] : 0;
-            const unsigned short hi = off[e + 1] >= 0 ? rs[off[e + 1] + pj * ps] : 0;
-            packed[e >> 1] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
-        }
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + pj * kstride + kv * 8);
         const size_t p = (static_cast<size_t>(t) * g + pi) * g + pj;
-        *reinterpret_cast<uint4*>(out + p * Kpad + k0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(out + p * Kpad + kv * 8) = v;
     }
 }
 
@@ -369,8 +379,10 @@ int im2col_patches(const void* px, int px_dtype, void* out, int T, int img, int 
     MJV_CHECK((reinterpret_cast<uintptr_t>(px) & 15) == 0, MJV_ERR_ARG, "im2col: pixel_values must be 16-byte aligned");
     const int g_ = img / ps;
     const int grid = T * g_;
-    const size_t smem = static_cast<size_t>(3) * ps * img * sizeof(__nv_bfloat16);
-    MJV_CHECK(smem <= 200 * 1024, MJV_ERR_ARG, "im2col: image rows do not fit in shared memory");
+    MJV_CHECK(ps % 2 == 0, MJV_ERR_ARG, "im2col: patch size %d must be even", ps);
+    const int kstride = Kpad + 8;   // +16 bytes: a patch row keeps its 16-byte alignment and successive patches shift by 4 banks
+    const size_t smem = static_cast<size_t>(g_) * kstride * sizeof(__nv_bfloat16);
+    MJV_CHECK(smem <= 200 * 1024, MJV_ERR_ARG, "im2col: one row of patches does not fit in shared memory");
     const int kvec = Kpad / 8;
     MJV_CHECK(kvec <= 512, MJV_ERR_ARG, "im2col: Kpad %d too large", Kpad);
     const int threads = kvec * (kvec >= 384 ? 1 : 384 / kvec);  // a multiple of kvec, ~384 threads
@@ -381,9 +393,9 @@ int im2col_patches(const void* px, int px_dtype, void* out, int T, int img, int 
     }
     LaunchScope scope(TAG_IM2COL, st, (double)T * (3.0 * img * img * (px_dtype == MJV_DTYPE_F32 ? 4 : 2) + 2.0 * g_ * g_ * Kpad));
     if (px_dtype == MJV_DTYPE_BF16)
-        im2col_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>((const __nv_bfloat16*)px, (__nv_bfloat16*)out, T, img, ps, Kpad);
+        im2col_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>((const __nv_bfloat16*)px, (__nv_bfloat16*)out, T, img, ps, Kpad, kstride);
     else if (px_dtype == MJV_DTYPE_F32)
-        im2col_kernel<float><<<grid, threads, smem, st>>>((const float*)px, (__nv_bfloat16*)out, T, img, ps, Kpad);
+        im2col_kernel<float><<<grid, threads, smem, st>>>((const float*)px, (__nv_bfloat16*)out, T, img, ps, Kpad, kstride);
     else
         return set_error(MJV_ERR_ARG, "im2col: unsupported pixel dtype %d", px_dtype);
     MJV_CUDA_OK(cudaGetLastError());

@@ -284,7 +284,7 @@ int launch_ln(const __nv_bfloat16* x, const __nv_bfloat16* w, const __nv_bfloat1
     MJV_CHECK(C % 8 == 0 && C <= 4096, MJV_ERR_ARG, "layernorm: C=%d unsupported", C);
     const int nchunk = (C + 255) / 256;
     // must match the W of the instantiation chosen below. (Two warps x 8 chunks for the 4096-wide projector LayerNorm
-    // measured slower in the step than four warps x 4 chunks: 0.374 vs 0.323 ms - the gathered rows want more rows in flight.)
+    // measured slower than four warps x 4 chunks, alone (4.10 vs 4.52 TB/s) and in the step; eight warps x 2 chunks: 4.19.)
     const int wpr = nchunk <= 4 ? 1 : (nchunk <= 8 ? 2 : 4);
     const int rows_per_block = kWarpsPerBlock / wpr;
     const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);

@@ -6,7 +6,8 @@
 // Why a second kernel (profiles/r01_ncu_full_attn_vit_v4.csv, source page): in attn_sm100.cuh a softmax warp spent only
 // 38 % of its time in the exponential loop; the rest was per-64-column-step overhead (barrier waits, spill reloads under
 // the 128-register cap of two CTAs per SM, instruction-cache misses of the doubly unrolled masked path, the item epilogue).
-// Here every step covers 128 columns, the two softmax warpgroups own 184 registers per thread (setmaxnreg), the masked
+// Here every step covers 128 columns, the two softmax warpgroups own 192 registers per thread (setmaxnreg; epilogue 72,
+// producer / issuers 56), the masked
 // path is a small pre-pass in front of the one exponential loop, and the O / l -> bf16 epilogue runs on its own
 // warpgroup while the softmax warps already work on the next item.
 //
@@ -23,6 +24,12 @@
 //     same query block - identical masks, shared K/V;
 //   * causal varlen mode otherwise (MHA, e.g. the Llama / Phi-3 shaped branch): two query blocks of one head, packed by the
 //     host in one work entry (low 16 bits: first block, high 16 bits: second block + 1, or 0 for none).
+// One exception shares nothing: with an odd number of query blocks and an even head count (ViT: 1025 rows = 8 blocks + 1
+// row) the last blocks of heads 2p and 2p + 1 form a "dual" item whose tiles read their own K / V (a stage per step).
+// Sequence lengths of 128 n + 1 in that mode also fold the last key in on the CUDA cores (AttnArgs.kv_tail) instead of
+// paying a block with one valid column. head_dim 128 keeps P in shared memory (one tile per query tile, SS-form P.V) and
+// hands the score buffer back as soon as it has been read (s_free); head_dim 64 writes P over S in TMEM (TS-form P.V).
+// Heads packed 96 columns apart run under the 128-wide tile with 6 of its 8 k-steps (AttnArgs.qk_stride / qk_ksteps).
 // Steps are numbered globally (g) in the order (block j, tile t) over the active tiles; step g uses score buffer
 // g % kNSB; S_{g+kNSB} (same buffer) is issued once pv_done signals that P_g·V has read P_g. The running maximum is updated lazily (only when it grows by more than 2^8), the rare rescale of
 // O_t happens in the softmax warps after waiting for the previous P·V of that tile (pv_done).

@@ -197,7 +197,24 @@ class InternVLChatRewardModeling(nn.Module):
         ps = list(self.parameters())
         return (ps[0].device, ps[0].dtype, sum(p._version for p in ps), tuple(p.data_ptr() for p in ps[:4]))
 
+    def release_module_weights(self) -> None:
+        """Inference-only memory saver. The engine holds its own re-packed copy of every weight, so after the first forward
+        a CUDA module carries the parameters twice (about 2 x 4.4 GB for MJ-VIDEO-2B). This moves the module's own
+        parameters and buffers to host memory and keeps scoring through the engine that was built from them; `state_dict()`
+        keeps working (CPU tensors). Moving the module back with `.cuda()` / loading new weights returns to the normal,
+        parameter-tracking behaviour. The reference has no equivalent: its module IS the only copy."""
+        eng = self._get_engine()
+        for t in list(self.parameters()) + list(self.buffers()):
+            t.data = t.data.to("cpu")
+        self._released_engine = eng
+        self._released_version = sum(p._version for p in self.parameters())
+
     def _get_engine(self) -> Engine:
+        released = getattr(self, "_released_engine", None)
+        if released is not None:
+            if self.model.device.type == "cpu" and sum(p._version for p in self.parameters()) == self._released_version:
+                return released
+            self._released_engine = None   # moved back to a device or modified: rebuild from the parameters
         dev = self.model.device
         if self._backbone_unloaded:
             some = sorted(self._backbone_unloaded)[:3]

@@ -99,6 +99,38 @@ def test_dropin_module_vs_reference_golden(gpu, golden_forward):
     _check(m.forward(pv.to(torch.bfloat16).cuda(), ids.cuda(), mask.cuda()), fix["outputs"])
 
 
+def test_release_module_weights_keeps_scoring(gpu):
+    """Inference-only memory saver: after release_module_weights() the module's parameters live on the host, the engine's
+    packed copy keeps scoring with identical bits, state_dict() still works, and .cuda() returns to the tracked behaviour."""
+    from mj_video_b200 import synth
+    from mj_video_b200.data_processor import load_video
+    from mj_video_b200.model import InternVLChatRewardModeling
+    d = synth.dims_tiny()
+    m = InternVLChatRewardModeling("unused", _tiny_cfg(d))
+    sd = synth.make_state_dict(d, seed=5)
+    m.load_state_dict(sd, strict=True)
+    m.config.pad_token_id = synth.PAD
+    m = m.to(torch.bfloat16).cuda().eval()
+    m.model.img_context_token_id = synth.IMG_CONTEXT
+    pv = torch.cat([load_video(synth.make_video(60 + i), num_segments=8, max_num=1)[0] for i in range(2)]).to(torch.bfloat16).cuda()
+    ids, mask = synth.pad_batch([synth.make_input_ids(i, [1] * 8, n_cap=n) for i, n in enumerate([12, 50])])
+    before = m.forward(pv, ids.cuda(), mask.cuda())
+    torch.cuda.synchronize()
+    mem0 = torch.cuda.memory_allocated()
+    m.release_module_weights()
+    assert all(p.device.type == "cpu" for p in m.parameters())
+    assert torch.cuda.memory_allocated() < mem0
+    after = m.forward(pv, ids.cuda(), mask.cuda())
+    for k in ("rewards", "aspect_scores", "score", "hidden_state"):
+        assert torch.equal(before[k], after[k]) and after[k].is_cuda
+    assert set(m.state_dict()) == set(sd)
+    g = m.aspect_gating(after.prompt_embedding)          # standalone operator still runs through the engine
+    assert torch.equal(g, after.aspect_gating_output)
+    m = m.cuda()                                         # back on the device: parameters are tracked again
+    again = m.forward(pv, ids.cuda(), mask.cuda())
+    assert torch.equal(before["score"], again["score"]) and getattr(m, "_released_engine", None) is None
+
+
 @pytest.fixture(scope="module")
 def tiny_engine(gpu):
     from mj_video_b200 import synth
